@@ -1,0 +1,72 @@
+"""ctypes binding of libmcosb200.so (the C ABI declared in include/mcosb.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is usable, the first call raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcosb200.so")
+
+N_STAGES = 7
+STAGE_NAMES = ("sample", "moments", "denoise", "markowitz", "hrp", "nco", "errors")
+
+MOMENTS_MUCOV, MOMENTS_LEDOIT_WOLF, MOMENTS_JACKKNIFE = 0, 1, 2
+ERR_EXPECTED_OUTCOME, ERR_VARIANCE, ERR_SHARPE = 0, 1, 2
+OPT_MARKOWITZ, OPT_HRP, OPT_NCO = 0, 1, 2
+
+ST_NOT_PD, ST_NO_EXCESS, ST_QP_CAP, ST_MPFIT_FAIL, ST_EIGVEC, ST_HRP_SUM, ST_NONFINITE = 1, 2, 4, 8, 16, 32, 64
+
+
+class MCOSBError(RuntimeError):
+    pass
+
+
+class Plan(ctypes.Structure):
+    _fields_ = [("moments_kind", c_int), ("denoise", c_int), ("bandwidth", c_double), ("n_optimizers", c_int),
+                ("optimizers", c_int * 4), ("error_kind", c_int), ("risk_free_rate", c_double),
+                ("nco_max_clusters", c_int), ("nco_trials", c_int), ("wave", c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/mcosb.h declares
+SIGNATURES = {
+    "mcosb_version": (c_int, []),
+    "mcosb_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_uint64]),
+    "mcosb_destroy": (c_int, [c_void_p]),
+    "mcosb_last_error": (c_char_p, [c_void_p]),
+    "mcosb_set_stream": (c_int, [c_void_p, c_void_p]),
+    "mcosb_synchronize": (c_int, [c_void_p]),
+    "mcosb_set_truth": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "mcosb_sample": (c_int, [c_void_p, c_uint64, c_int, c_void_p]),
+    "mcosb_moments": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mcosb_denoise": (c_int, [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcosb_markowitz": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "mcosb_hrp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcosb_nco": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcosb_errors": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcosb_run": (c_int, [c_void_p, POINTER(Plan), c_uint64, c_int, c_void_p, c_void_p]),
+    "mcosb_last_stage_ms": (c_int, [c_void_p, POINTER(c_double)]),
+    "mcosb_launch_count": (c_longlong, [c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the library once and types every entry point. Raises MCOSBError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MCOSBError(f"{LIB_PATH} is missing: build it with `make -C mcos_b200/csrc` "
+                         "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise MCOSBError(f"{LIB_PATH} does not export {name}") from exc
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib

@@ -1,0 +1,235 @@
+// Context lifetime, truth upload (+ one-off Cholesky), and the error-estimator kernel (K5).
+#include "common.cuh"
+
+extern "C" int mcosb_version(void) { return 100; }
+
+extern "C" int mcosb_create(mcosb_ctx** out, int device, int n_assets, int n_obs, uint64_t seed) {
+    if (!out || n_assets < 1 || n_obs < 1) return MCOSB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return MCOSB_ERR_CUDA;  // no CPU fallback, by design
+    if (device < 0 || device >= count) return MCOSB_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return MCOSB_ERR_CUDA;
+    mcosb_ctx* ctx = new mcosb_ctx();
+    ctx->device = device;
+    ctx->N = n_assets;
+    ctx->T = n_obs;
+    ctx->seed = seed;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return MCOSB_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    size_t n = (size_t)n_assets;
+    if (cudaMalloc(&ctx->d_mu, n * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_cov, n * n * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_chol, n * n * sizeof(double)) != cudaSuccess) {
+        mcosb_destroy(ctx);
+        return MCOSB_ERR_CUDA;
+    }
+    *out = ctx;
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_destroy(mcosb_ctx* ctx) {
+    if (!ctx) return MCOSB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < SL_COUNT; ++i)
+        if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    if (ctx->d_mu) cudaFree(ctx->d_mu);
+    if (ctx->d_cov) cudaFree(ctx->d_cov);
+    if (ctx->d_chol) cudaFree(ctx->d_chol);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MCOSB_OK;
+}
+
+extern "C" const char* mcosb_last_error(const mcosb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int mcosb_set_stream(mcosb_ctx* ctx, void* cuda_stream) {
+    MCOSB_CHECK_CTX(ctx);
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_synchronize(mcosb_ctx* ctx) {
+    MCOSB_CHECK_CTX(ctx);
+    MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCOSB_OK;
+}
+
+extern "C" long long mcosb_launch_count(const mcosb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int mcosb_last_stage_ms(mcosb_ctx* ctx, double* stage_ms) {
+    if (!ctx || !stage_ms) return MCOSB_ERR_ARG;
+    for (int i = 0; i < MCOSB_N_STAGES; ++i) stage_ms[i] = ctx->stage_ms[i];
+    return MCOSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One-off Cholesky of the true covariance (single CTA, right-looking, in place on a copy). Runs once per truth.
+// flag[0] is set to 1 when a pivot is not positive.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) chol_truth_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
+    __shared__ double s_piv;
+    for (int k = 0; k < n; ++k) {
+        if (threadIdx.x == 0) {
+            double d = L[(size_t)k * n + k];
+            if (!(d > 0.0)) { flag[0] = 1; d = 1.0; }
+            s_piv = sqrt(d);
+            L[(size_t)k * n + k] = s_piv;
+        }
+        __syncthreads();
+        double piv = s_piv;
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) L[(size_t)i * n + k] /= piv;
+        __syncthreads();
+        // trailing update of the lower triangle: L[i][j] -= L[i][k] * L[j][k], k < j <= i
+        int m = n - k - 1;
+        for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+            int i = k + 1 + idx / m, j = k + 1 + idx % m;
+            if (j <= i) L[(size_t)i * n + j] -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
+        }
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        int i = idx / n, j = idx % n;
+        if (j > i) L[idx] = 0.0;
+    }
+}
+
+extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* cov) {
+    MCOSB_CHECK_CTX(ctx);
+    if (!mu || !cov) return mcosb_fail(ctx, MCOSB_ERR_ARG, "mu/cov must not be null");
+    size_t n = (size_t)ctx->N;
+    cudaMemcpyKind kmu = mcosb_is_device_ptr(mu) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaMemcpyKind kcov = mcosb_is_device_ptr(cov) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    MCOSB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mu, mu, n * sizeof(double), kmu, ctx->stream));
+    MCOSB_CUDA(ctx, cudaMemcpyAsync(ctx->d_cov, cov, n * n * sizeof(double), kcov, ctx->stream));
+    MCOSB_CUDA(ctx, cudaMemcpyAsync(ctx->d_chol, ctx->d_cov, n * n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
+    int* dflag = nullptr;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, 1, &dflag));
+    MCOSB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
+    chol_truth_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_chol, ctx->N, dflag);
+    MCOSB_LAUNCHED(ctx);
+    int flag = 0;
+    MCOSB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_truth = true;  // mu/cov are usable by the estimators even if sampling is not
+    if (flag) return mcosb_fail(ctx, MCOSB_ERR_NOT_PD, "true covariance is not positive definite");
+    return MCOSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5: error estimators (error_estimator.py:21-49).  delta = w* - w;  EO = delta.mu;  Var = delta' Cov delta.
+// One CTA handles ERR_SB simulations so each row of the true covariance read from L2 is reused ERR_SB times.
+// ---------------------------------------------------------------------------------------------------------------
+#define ERR_SB 8
+#define ERR_THREADS 256
+
+__global__ void __launch_bounds__(ERR_THREADS) errors_kernel(const double* __restrict__ w,
+                                                             const double* __restrict__ wstar, int batched,
+                                                             const double* __restrict__ mu,
+                                                             const double* __restrict__ cov, int n, int S, int kind,
+                                                             double* __restrict__ err) {
+    extern __shared__ double sm[];
+    double* delta = sm;                  // [ERR_SB][n]
+    double* red = sm + (size_t)ERR_SB * n;  // [ERR_THREADS/32][ERR_SB][2]
+    const int s0 = blockIdx.x * ERR_SB;
+    const int ns = min(ERR_SB, S - s0);
+    for (int idx = threadIdx.x; idx < ERR_SB * n; idx += blockDim.x) {
+        int s = idx / n, j = idx % n;
+        double d = 0.0;
+        if (s < ns) {
+            double ws = batched ? wstar[(size_t)(s0 + s) * n + j] : wstar[j];
+            d = ws - w[(size_t)(s0 + s) * n + j];
+        }
+        delta[idx] = d;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double var_acc[ERR_SB], eo_acc[ERR_SB];
+#pragma unroll
+    for (int s = 0; s < ERR_SB; ++s) var_acc[s] = eo_acc[s] = 0.0;
+    if (kind != MCOSB_ERR_EXPECTED_OUTCOME) {
+        for (int i = wid; i < n; i += nw) {
+            double t[ERR_SB];
+#pragma unroll
+            for (int s = 0; s < ERR_SB; ++s) t[s] = 0.0;
+            const double* row = cov + (size_t)i * n;
+            for (int j = lane; j < n; j += 32) {
+                double c = row[j];
+#pragma unroll
+                for (int s = 0; s < ERR_SB; ++s) t[s] = fma(c, delta[s * n + j], t[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < ERR_SB; ++s) {
+                double v = warp_sum(t[s]);
+                var_acc[s] = fma(delta[s * n + i], v, var_acc[s]);  // identical on all lanes
+            }
+        }
+    }
+    if (kind != MCOSB_ERR_VARIANCE) {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            double m = mu[j];
+#pragma unroll
+            for (int s = 0; s < ERR_SB; ++s) eo_acc[s] = fma(delta[s * n + j], m, eo_acc[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < ERR_SB; ++s) eo_acc[s] = warp_sum(eo_acc[s]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < ERR_SB; ++s) {
+            red[(wid * ERR_SB + s) * 2 + 0] = var_acc[s];
+            red[(wid * ERR_SB + s) * 2 + 1] = eo_acc[s];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ns) {
+        int s = threadIdx.x;
+        double var = 0.0, eo = 0.0;
+        for (int k = 0; k < nw; ++k) {
+            var += red[(k * ERR_SB + s) * 2 + 0];
+            eo += red[(k * ERR_SB + s) * 2 + 1];
+        }
+        double out;
+        if (kind == MCOSB_ERR_EXPECTED_OUTCOME) out = eo;
+        else if (kind == MCOSB_ERR_VARIANCE) out = var;
+        else out = eo / sqrt(var);
+        err[s0 + s] = out;
+    }
+}
+
+int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int kind,
+                     double* derr) {
+    if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
+    if (kind < 0 || kind > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown error estimator kind");
+    if (S == 0) return MCOSB_OK;
+    size_t smem = ((size_t)ERR_SB * ctx->N + (ERR_THREADS / 32) * ERR_SB * 2) * sizeof(double);
+    if (smem > 48 * 1024)
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(errors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (S + ERR_SB - 1) / ERR_SB;
+    errors_kernel<<<grid, ERR_THREADS, smem, ctx->stream>>>(dw, dwstar, batched, ctx->d_mu, ctx->d_cov, ctx->N, S,
+                                                           kind, derr);
+    MCOSB_LAUNCHED(ctx);
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_errors(mcosb_ctx* ctx, int S, const double* w, const double* w_star, int w_star_batched,
+                            int kind, double* err) {
+    MCOSB_CHECK_CTX(ctx);
+    if (S < 0 || !w || !w_star || !err) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_errors");
+    size_t n = (size_t)ctx->N;
+    Staging st(ctx);
+    const double *dw, *dws;
+    double* derr;
+    MCOSB_TRY(st.in(w, (size_t)S * n, SL_STAGE_IN0, &dw));
+    MCOSB_TRY(st.in(w_star, w_star_batched ? (size_t)S * n : n, SL_STAGE_IN1, &dws));
+    MCOSB_TRY(st.out(err, (size_t)S, SL_STAGE_OUT0, &derr));
+    MCOSB_TRY(mcosb_dev_errors(ctx, S, dw, dws, w_star_batched, kind, derr));
+    return st.finish();
+}

@@ -1,0 +1,205 @@
+// Shared internals of libmcosb200: context, scratch arena, host/device pointer staging, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mcosb.h"
+
+#define MCOSB_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+enum ScratchSlot {
+    SL_STAGE_IN0 = 0, SL_STAGE_IN1, SL_STAGE_IN2, SL_STAGE_IN3,
+    SL_STAGE_OUT0, SL_STAGE_OUT1, SL_STAGE_OUT2, SL_STAGE_OUT3, SL_STAGE_OUT4,
+    SL_Z, SL_X, SL_MUHAT, SL_COV, SL_COLMEAN, SL_LWPART, SL_LWSTAT,
+    SL_DN_A, SL_DN_SIGMA, SL_DN_D, SL_DN_E, SL_DN_TAU, SL_DN_LAM, SL_DN_VAR, SL_DN_NF, SL_DN_VEC, SL_DN_WORK,
+    SL_MK_L, SL_MK_W, SL_MK_ITERS,
+    SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
+    SL_NCO_W, SL_NCO_LABELS, SL_NCO_WORK, SL_NCO_E,
+    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W,
+    SL_COUNT
+};
+
+struct mcosb_ctx {
+    int device = 0;
+    int N = 0, T = 0;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    double* d_mu = nullptr;    // true mu [N]
+    double* d_cov = nullptr;   // true cov [N][N]
+    double* d_chol = nullptr;  // lower Cholesky factor of the true cov [N][N]
+    bool have_truth = false;
+    void* slot_ptr[SL_COUNT] = {};
+    size_t slot_bytes[SL_COUNT] = {};
+    std::string err;
+    long long launches = 0;
+    double stage_ms[MCOSB_N_STAGES] = {};
+    int smem_optin = 0;
+    int num_sms = MCOSB_SMS;
+};
+
+inline int mcosb_fail(mcosb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define MCOSB_CUDA(ctx, call)                                                                        \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char buf__[512];                                                                         \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                     __FILE__, __LINE__);                                                            \
+            return mcosb_fail(ctx, MCOSB_ERR_CUDA, buf__);                                           \
+        }                                                                                            \
+    } while (0)
+
+#define MCOSB_TRY(expr)            \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != MCOSB_OK) return rc__; \
+    } while (0)
+
+// After every kernel launch: count it and surface launch-configuration errors immediately.
+#define MCOSB_LAUNCHED(ctx)                      \
+    do {                                         \
+        (ctx)->launches++;                       \
+        MCOSB_CUDA(ctx, cudaGetLastError());     \
+    } while (0)
+
+// Grow-only device scratch, one buffer per slot.
+inline int mcosb_scratch(mcosb_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 8;
+    if (ctx->slot_bytes[slot] < bytes) {
+        if (ctx->slot_ptr[slot]) {
+            MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            MCOSB_CUDA(ctx, cudaFree(ctx->slot_ptr[slot]));
+            ctx->slot_ptr[slot] = nullptr;
+            ctx->slot_bytes[slot] = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        MCOSB_CUDA(ctx, cudaMalloc(&ctx->slot_ptr[slot], want));
+        ctx->slot_bytes[slot] = want;
+    }
+    *out = ctx->slot_ptr[slot];
+    return MCOSB_OK;
+}
+
+template <typename T>
+inline int mcosb_scratch_t(mcosb_ctx* ctx, int slot, size_t count, T** out) {
+    void* p = nullptr;
+    MCOSB_TRY(mcosb_scratch(ctx, slot, count * sizeof(T), &p));
+    *out = static_cast<T*>(p);
+    return MCOSB_OK;
+}
+
+inline bool mcosb_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Tracks host buffers staged through device scratch within one API call.
+struct Staging {
+    mcosb_ctx* ctx;
+    struct Out { void* host; void* dev; size_t bytes; };
+    std::vector<Out> outs;
+    bool any_host = false;
+    explicit Staging(mcosb_ctx* c) : ctx(c) {}
+
+    // Input: returns a device pointer holding `bytes` of `p` (p itself if it already is one). nullptr stays nullptr.
+    template <typename T>
+    int in(const T* p, size_t count, int slot, const T** out) {
+        if (!p) { *out = nullptr; return MCOSB_OK; }
+        if (mcosb_is_device_ptr(p)) { *out = p; return MCOSB_OK; }
+        any_host = true;
+        T* d = nullptr;
+        MCOSB_TRY(mcosb_scratch_t(ctx, slot, count, &d));
+        MCOSB_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        *out = d;
+        return MCOSB_OK;
+    }
+    // Output: device pointer to write into; copied back to the host buffer by finish().
+    template <typename T>
+    int out(T* p, size_t count, int slot, T** outp) {
+        if (!p) { *outp = nullptr; return MCOSB_OK; }
+        if (mcosb_is_device_ptr(p)) { *outp = p; return MCOSB_OK; }
+        any_host = true;
+        T* d = nullptr;
+        MCOSB_TRY(mcosb_scratch_t(ctx, slot, count, &d));
+        outs.push_back({p, d, count * sizeof(T)});
+        *outp = d;
+        return MCOSB_OK;
+    }
+    // In/out buffer.
+    template <typename T>
+    int inout(T* p, size_t count, int slot, T** outp) {
+        if (!p) { *outp = nullptr; return MCOSB_OK; }
+        if (mcosb_is_device_ptr(p)) { *outp = p; return MCOSB_OK; }
+        any_host = true;
+        T* d = nullptr;
+        MCOSB_TRY(mcosb_scratch_t(ctx, slot, count, &d));
+        MCOSB_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        outs.push_back({p, d, count * sizeof(T)});
+        *outp = d;
+        return MCOSB_OK;
+    }
+    int finish() {
+        for (auto& o : outs)
+            MCOSB_CUDA(ctx, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (any_host) MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MCOSB_OK;
+    }
+};
+
+#define MCOSB_CHECK_CTX(ctx)                          \
+    do {                                              \
+        if (!(ctx)) return MCOSB_ERR_ARG;             \
+        cudaError_t e__ = cudaSetDevice((ctx)->device); \
+        if (e__ != cudaSuccess) return mcosb_fail(ctx, MCOSB_ERR_CUDA, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum; `red` must hold >= 32 doubles of shared memory. All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect red from a previous use
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    double t = (lane < nw) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// internal (device-pointer) stage entry points used by the public wrappers and by mcosb_run
+// ---------------------------------------------------------------------------------------------------------------
+int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX);
+int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink);
+int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
+                      int* dnf, int* dstatus);
+int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, double rf, int clean,
+                        double* dw, int* diters, int* dstatus);
+int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* dorder, double* dlink, int* dstatus);
+int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, int max_k, int trials,
+                  const int* dlabels_in, double* dw, int* dlabels_out, int* dstatus);
+int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int kind,
+                     double* derr);

@@ -1,0 +1,254 @@
+// K2: batched mean + sample covariance (FP64 tensor-core SYRK) with the Ledoit-Wolf and jackknife estimators as
+// fused reductions.  Replaces observation_simulator.py:28 (LedoitWolf().fit), :40 (np.cov), :53-57 (jackknife loops).
+//
+//   mean_j   = sum_t X[t][j] / T
+//   S        = Xc' Xc / (T-1)                         (MuCov; Jackknife collapses to the same thing)
+//   S_b      = Xc' Xc / T, shrunk to (1-d) S_b + d m I (Ledoit-Wolf, SURVEY A.3 / sklearn _shrunk_covariance.py)
+//
+// HBM/L2 traffic per simulation: X read twice (mean pass + SYRK; 2 x 8TN bytes, three times for Ledoit-Wolf), cov
+// written once (8N^2), plus one read-modify-write of cov for the Ledoit-Wolf shrink.  Flops: 2 T N^2 / 2 (lower tiles).
+#include "common.cuh"
+#include "dmma.cuh"
+
+#define CM_COLS 32
+#define CM_ROWGROUPS 8
+
+__global__ void __launch_bounds__(CM_COLS* CM_ROWGROUPS) colmean_kernel(const double* __restrict__ X, int T, int N,
+                                                                        double* __restrict__ mean) {
+    __shared__ double part[CM_ROWGROUPS][CM_COLS];
+    const int s = blockIdx.y;
+    const int col = blockIdx.x * CM_COLS + (threadIdx.x % CM_COLS);
+    const int rg = threadIdx.x / CM_COLS;
+    const double* x = X + (size_t)s * T * N;
+    double acc = 0.0;
+    if (col < N)
+        for (int t = rg; t < T; t += CM_ROWGROUPS) acc += x[(size_t)t * N + col];
+    part[rg][threadIdx.x % CM_COLS] = acc;
+    __syncthreads();
+    if (rg == 0 && col < N) {
+        double tot = 0.0;
+#pragma unroll
+        for (int r = 0; r < CM_ROWGROUPS; ++r) tot += part[r][threadIdx.x];
+        mean[(size_t)s * N + col] = tot / (double)T;
+    }
+}
+
+// Lower-triangle tile p -> (I, J), I >= J
+__device__ __forceinline__ void tile_ij(int p, int& I, int& J) {
+    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= p) ++i;
+    while (i * (i + 1) / 2 > p) --i;
+    I = i;
+    J = p - i * (i + 1) / 2;
+}
+
+// grid = (lower tiles, S).  lwpart[s][tile][2] receives (sum of squares of the scaled entries this tile stands for in
+// the full symmetric matrix, trace contribution).
+__global__ void __launch_bounds__(DM_THREADS, 1)
+syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T, int N, double scale,
+            double* __restrict__ cov, double* __restrict__ lwpart) {
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    const int s = blockIdx.y;
+    int I, J;
+    tile_ij(blockIdx.x, I, J);
+    const bool diag = (I == J);
+    const double* x = X + (size_t)s * T * N;
+    const double* mu = mean + (size_t)s * N;
+    double* As[2] = {sm, sm + 2 * DM_BK * DM_LD_KMAJOR};
+    double* Bs[2] = {sm + DM_BK * DM_LD_KMAJOR, sm + 3 * DM_BK * DM_LD_KMAJOR};
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
+    const int lcol = tid % DM_BM, lk = tid / DM_BM;  // loader mapping: column fixed, k = lk + 2r
+    const int acol = I * DM_BM + lcol, bcol = J * DM_BN + lcol;
+    const double amean = (acol < N) ? mu[acol] : 0.0;
+    const double bmean = (bcol < N) ? mu[bcol] : 0.0;
+
+    double acc[DM_MB][DM_NB][2];
+#pragma unroll
+    for (int a = 0; a < DM_MB; ++a)
+#pragma unroll
+        for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    double ra[DM_BK / 2], rb[DM_BK / 2];
+    auto gload = [&](int kbase) {
+#pragma unroll
+        for (int r = 0; r < DM_BK / 2; ++r) {
+            int k = kbase + lk + 2 * r;
+            bool ok = k < T;
+            ra[r] = (ok && acol < N) ? x[(size_t)k * N + acol] - amean : 0.0;
+            if (!diag) rb[r] = (ok && bcol < N) ? x[(size_t)k * N + bcol] - bmean : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < DM_BK / 2; ++r) {
+            int k = lk + 2 * r;
+            As[buf][k * DM_LD_KMAJOR + lcol] = ra[r];
+            if (!diag) Bs[buf][k * DM_LD_KMAJOR + lcol] = rb[r];
+        }
+    };
+
+    const int nkt = (T + DM_BK - 1) / DM_BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) gload((kt + 1) * DM_BK);
+        dmma_slab<true, true>(As[buf], diag ? As[buf] : Bs[buf], wm0, wn0, lane, acc);
+        if (kt + 1 < nkt) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+    // epilogue: scale, write the lower part and its mirror, accumulate Frobenius / trace partials
+    const int g = lane >> 2, t4 = lane & 3;
+    double* c = cov + (size_t)s * N * N;
+    double frob = 0.0, tr = 0.0;
+#pragma unroll
+    for (int mb = 0; mb < DM_MB; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < DM_NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int row = I * DM_BM + wm0 + mb * 8 + g;
+                int col = J * DM_BN + wn0 + nb * 8 + 2 * t4 + e;
+                if (row < N && col < N && col <= row) {
+                    double v = acc[mb][nb][e] * scale;
+                    c[(size_t)row * N + col] = v;
+                    if (col != row) {
+                        c[(size_t)col * N + row] = v;
+                        frob += 2.0 * v * v;
+                    } else {
+                        frob += v * v;
+                        tr += v;
+                    }
+                }
+            }
+    if (lwpart) {
+        frob = block_sum(frob, red);
+        tr = block_sum(tr, red);
+        if (tid == 0) {
+            size_t o = ((size_t)s * gridDim.x + blockIdx.x) * 2;
+            lwpart[o] = frob;
+            lwpart[o + 1] = tr;
+        }
+    }
+}
+
+// Ledoit-Wolf beta_raw = sum_t (sum_i xc_ti^2)^2, partial per chunk of rows.  grid = (row chunks, S)
+#define RN_ROWS 64
+__global__ void __launch_bounds__(256) lw_rownorm_kernel(const double* __restrict__ X,
+                                                         const double* __restrict__ mean, int T, int N,
+                                                         double* __restrict__ part) {
+    __shared__ double red[32];
+    const int s = blockIdx.y;
+    const double* x = X + (size_t)s * T * N;
+    const double* mu = mean + (size_t)s * N;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (int r = wid; r < RN_ROWS; r += 8) {
+        int t = blockIdx.x * RN_ROWS + r;
+        if (t >= T) break;
+        double q = 0.0;
+        for (int j = lane; j < N; j += 32) {
+            double d = x[(size_t)t * N + j] - mu[j];
+            q = fma(d, d, q);
+        }
+        q = warp_sum(q);
+        acc += q * q;  // identical on all lanes
+    }
+    double tot = block_sum(lane == 0 ? acc : 0.0, red);
+    if (threadIdx.x == 0) part[(size_t)s * gridDim.x + blockIdx.x] = tot;
+}
+
+// Finishes Ledoit-Wolf: shrinkage from the partials, then cov <- (1-d) cov + d m I in place.  grid = S
+__global__ void __launch_bounds__(256) lw_finish_kernel(double* __restrict__ cov, const double* __restrict__ lwpart,
+                                                        int ntiles, const double* __restrict__ rnpart, int nchunks,
+                                                        int T, int N, double* __restrict__ shrink_out) {
+    __shared__ double s_shrink, s_m;
+    const int s = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double delta_raw = 0.0, tr = 0.0, beta_raw = 0.0;
+        for (int i = 0; i < ntiles; ++i) {
+            delta_raw += lwpart[((size_t)s * ntiles + i) * 2];
+            tr += lwpart[((size_t)s * ntiles + i) * 2 + 1];
+        }
+        for (int i = 0; i < nchunks; ++i) beta_raw += rnpart[(size_t)s * nchunks + i];
+        double m = tr / N;
+        double beta = (beta_raw / T - delta_raw) / ((double)N * T);
+        double delta = (delta_raw - N * m * m) / N;
+        beta = fmin(beta, delta);
+        double sh = (beta == 0.0) ? 0.0 : beta / delta;
+        s_shrink = sh;
+        s_m = m;
+        if (shrink_out) shrink_out[s] = sh;
+    }
+    __syncthreads();
+    const double sh = s_shrink, m = s_m;
+    double* c = cov + (size_t)s * N * N;
+    for (size_t idx = threadIdx.x; idx < (size_t)N * N; idx += blockDim.x) {
+        double v = (1.0 - sh) * c[idx];
+        if (idx / N == idx % N) v += sh * m;
+        c[idx] = v;
+    }
+}
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink) {
+    if (kind < 0 || kind > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown moments kind");
+    if (S == 0) return MCOSB_OK;
+    const int N = ctx->N, T = ctx->T;
+    if (kind == MCOSB_MOMENTS_JACKKNIFE && T < 3)
+        return mcosb_fail(ctx, MCOSB_ERR_ARG, "jackknife needs at least 3 observations");
+    if (kind == MCOSB_MOMENTS_MUCOV && T < 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "covariance needs T >= 2");
+    const bool lw = (kind == MCOSB_MOMENTS_LEDOIT_WOLF);
+
+    dim3 gm((N + CM_COLS - 1) / CM_COLS, S);
+    colmean_kernel<<<gm, CM_COLS * CM_ROWGROUPS, 0, ctx->stream>>>(dX, T, N, dmu);
+    MCOSB_LAUNCHED(ctx);
+
+    const int nt = (N + DM_BM - 1) / DM_BM, ntiles = nt * (nt + 1) / 2;
+    double* lwpart = nullptr;
+    if (lw) MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWPART, (size_t)S * ntiles * 2, &lwpart));
+    const size_t smem = (size_t)4 * DM_BK * DM_LD_KMAJOR * sizeof(double);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double scale = lw ? 1.0 / T : 1.0 / (T - 1);
+    syrk_kernel<<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
+    MCOSB_LAUNCHED(ctx);
+
+    if (lw) {
+        const int nchunks = (T + RN_ROWS - 1) / RN_ROWS;
+        double* rnpart = nullptr;
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWSTAT, (size_t)S * nchunks, &rnpart));
+        lw_rownorm_kernel<<<dim3(nchunks, S), 256, 0, ctx->stream>>>(dX, dmu, T, N, rnpart);
+        MCOSB_LAUNCHED(ctx);
+        lw_finish_kernel<<<S, 256, 0, ctx->stream>>>(dcov, lwpart, ntiles, rnpart, nchunks, T, N, dshrink);
+        MCOSB_LAUNCHED(ctx);
+    } else if (dshrink) {
+        fill_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(dshrink, (size_t)S, 0.0);
+        MCOSB_LAUNCHED(ctx);
+    }
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_moments(mcosb_ctx* ctx, int S, const double* X, int kind, double* mu_hat, double* cov_hat,
+                             double* shrink) {
+    MCOSB_CHECK_CTX(ctx);
+    if (S < 0 || !X || !mu_hat || !cov_hat) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_moments");
+    const size_t N = ctx->N, T = ctx->T;
+    Staging st(ctx);
+    const double* dX;
+    double *dmu, *dcov, *dsh;
+    MCOSB_TRY(st.in(X, (size_t)S * T * N, SL_STAGE_IN0, &dX));
+    MCOSB_TRY(st.out(mu_hat, (size_t)S * N, SL_STAGE_OUT0, &dmu));
+    MCOSB_TRY(st.out(cov_hat, (size_t)S * N * N, SL_STAGE_OUT1, &dcov));
+    MCOSB_TRY(st.out(shrink, (size_t)S, SL_STAGE_OUT2, &dsh));
+    MCOSB_TRY(mcosb_dev_moments(ctx, S, dX, kind, dmu, dcov, dsh));
+    return st.finish();
+}

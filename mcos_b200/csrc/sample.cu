@@ -1,0 +1,153 @@
+// K1: Philox4x32-10 sampling of T x N multivariate-normal observations, X = mu + Z L' with L the once-computed
+// Cholesky factor of the true covariance.  Replaces np.random.multivariate_normal (observation_simulator.py:27,39,51),
+// which re-does an SVD of the true covariance on every call.
+//
+//   philox_normal_kernel : Z[s][t][2p..2p+1] = Box-Muller(Philox4x32-10(counter = (sim lo, sim hi, t, p), key = seed))
+//                          -> pure RNG, one 128-bit Philox block per pair of normals; bound by the FP64 log/sincos
+//                          pipe and by the 8TN bytes it writes.
+//   trmm_kernel          : X = mu + Z L'  as one (S*T) x N x N FP64 tensor-core GEMM over all simulations at once
+//                          (L is shared), skipping the k-slabs above the diagonal.  Flops 2 * T * N^2 / 2.
+#include "common.cuh"
+#include "dmma.cuh"
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Two standard normals from one Philox block: u1 in (0,1], u2 in [0,1) from 2 x 64 bits (top 53 used).
+__device__ __forceinline__ void normal_pair(uint64_t sim, uint32_t t, uint32_t p, uint64_t seed, double& z0,
+                                            double& z1) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)sim, (uint32_t)(sim >> 32), t, p, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    uint64_t a = ((uint64_t)r[1] << 32) | r[0];
+    uint64_t b = ((uint64_t)r[3] << 32) | r[2];
+    double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
+    double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+    double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+// grid-stride over pairs; Z is [S][T][N]
+__global__ void __launch_bounds__(256) philox_normal_kernel(double* __restrict__ Z, uint64_t sim_id0, int S, int T,
+                                                            int N, uint64_t seed) {
+    const int P = (N + 1) / 2;  // pairs per row
+    const size_t total = (size_t)S * T * P;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        uint32_t p = (uint32_t)(idx % P);
+        size_t row = idx / P;
+        uint32_t t = (uint32_t)(row % T);
+        uint64_t s = row / T;
+        double z0, z1;
+        normal_pair(sim_id0 + s, t, p, seed, z0, z1);
+        double* dst = Z + row * N + 2 * (size_t)p;
+        dst[0] = z0;
+        if (2 * p + 1 < (uint32_t)N) dst[1] = z1;
+    }
+}
+
+// X[m][j] = mu[j] + sum_{k <= j} Z[m][k] L[j][k];  M = S*T rows.  grid = (col tiles, row tiles)
+__global__ void __launch_bounds__(DM_THREADS, 1)
+trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const double* __restrict__ mu, size_t M, int N,
+            double* __restrict__ X) {
+    extern __shared__ double sm[];
+    const int J = blockIdx.x;
+    const size_t m0 = (size_t)blockIdx.y * DM_BM;
+    double* As[2] = {sm, sm + 2 * DM_BM * DM_LD_MMAJOR};
+    double* Bs[2] = {sm + DM_BM * DM_LD_MMAJOR, sm + 3 * DM_BM * DM_LD_MMAJOR};
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
+    const int lk = tid % DM_BK, lr = tid / DM_BK;  // loader: k fixed, row = lr + 16 r
+
+    double acc[DM_MB][DM_NB][2];
+#pragma unroll
+    for (int a = 0; a < DM_MB; ++a)
+#pragma unroll
+        for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    double ra[8], rb[8];
+    auto gload = [&](int kbase) {
+        int k = kbase + lk;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            size_t m = m0 + lr + 16 * r;
+            int j = J * DM_BN + lr + 16 * r;
+            ra[r] = (k < N && m < M) ? Z[m * N + k] : 0.0;
+            rb[r] = (k < N && j < N) ? L[(size_t)j * N + k] : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            As[buf][(lr + 16 * r) * DM_LD_MMAJOR + lk] = ra[r];
+            Bs[buf][(lr + 16 * r) * DM_LD_MMAJOR + lk] = rb[r];
+        }
+    };
+    const int kend = min(N, (J + 1) * DM_BN);  // L[j][k] = 0 for k > j
+    const int nkt = (kend + DM_BK - 1) / DM_BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) gload((kt + 1) * DM_BK);
+        dmma_slab<false, false>(As[buf], Bs[buf], wm0, wn0, lane, acc);
+        if (kt + 1 < nkt) sstore(buf ^ 1);
+        __syncthreads();
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int mb = 0; mb < DM_MB; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < DM_NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                size_t row = m0 + wm0 + mb * 8 + g;
+                int col = J * DM_BN + wn0 + nb * 8 + 2 * t4 + e;
+                if (row < M && col < N) X[row * N + col] = acc[mb][nb][e] + mu[col];
+            }
+}
+
+int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
+    if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
+    if (S == 0) return MCOSB_OK;
+    const int N = ctx->N, T = ctx->T;
+    const size_t M = (size_t)S * T;
+    double* dZ = nullptr;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_Z, M * N, &dZ));
+    size_t pairs = M * ((N + 1) / 2);
+    int grid = (int)std::min<size_t>((pairs + 255) / 256, (size_t)ctx->num_sms * 16);
+    philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
+    MCOSB_LAUNCHED(ctx);
+    const size_t smem = (size_t)4 * DM_BM * DM_LD_MMAJOR * sizeof(double);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t row_tiles = (M + DM_BM - 1) / DM_BM;
+    if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");
+    dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
+    trmm_kernel<<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+    MCOSB_LAUNCHED(ctx);
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* X) {
+    MCOSB_CHECK_CTX(ctx);
+    if (S < 0 || !X) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_sample");
+    Staging st(ctx);
+    double* dX;
+    MCOSB_TRY(st.out(X, (size_t)S * ctx->T * ctx->N, SL_STAGE_OUT0, &dX));
+    MCOSB_TRY(mcosb_dev_sample(ctx, sim_id0, S, dX));
+    return st.finish();
+}

@@ -92,7 +92,10 @@ def main():
     opt_lits = literal_arrays(f"{REF}/tests/test_optimizer.py")
     ct_lits = literal_arrays(f"{REF}/tests/test_covariance_transformer.py")
     ee_lits = literal_arrays(f"{REF}/tests/test_error_estimator.py")
-    by_line = {ln: v for ln, v in opt_lits}
+    by_line = {}
+    for ln, v in opt_lits:
+        if ln not in by_line or v.size > by_line[ln].size:
+            by_line[ln] = v
     lit = {
         "markowitz_w": by_line[17], "nco_max_sharpe_w": by_line[35], "nco_min_var_w": by_line[44],
         "hrp_w": by_line[61], "rp_cov": by_line[73], "rp_w": by_line[82], "rp_budget": by_line[85],
