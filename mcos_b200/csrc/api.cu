@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(ERR_THREADS) errors_kernel(const double* __res
                                                              const double* __restrict__ wstar, int batched,
                                                              const double* __restrict__ mu,
                                                              const double* __restrict__ cov, int n, int S, int kind,
-                                                             double* __restrict__ err) {
+                                                             double* __restrict__ err, int ld) {
     extern __shared__ double sm[];
     double* delta = sm;                  // [ERR_SB][n]
     double* red = sm + (size_t)ERR_SB * n;  // [ERR_THREADS/32][ERR_SB][2]
@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(ERR_THREADS) errors_kernel(const double* __res
         if (kind == MCOSB_ERR_EXPECTED_OUTCOME) out = eo;
         else if (kind == MCOSB_ERR_VARIANCE) out = var;
         else out = eo / sqrt(var);
-        err[s0 + s] = out;
+        err[(size_t)(s0 + s) * ld] = out;
     }
 }
 
 int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int kind,
-                     double* derr) {
+                     double* derr, int ld) {
     if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
     if (kind < 0 || kind > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown error estimator kind");
     if (S == 0) return MCOSB_OK;
@@ -214,7 +214,7 @@ int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwst
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(errors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (S + ERR_SB - 1) / ERR_SB;
     errors_kernel<<<grid, ERR_THREADS, smem, ctx->stream>>>(dw, dwstar, batched, ctx->d_mu, ctx->d_cov, ctx->N, S,
-                                                           kind, derr);
+                                                           kind, derr, ld);
     MCOSB_LAUNCHED(ctx);
     return MCOSB_OK;
 }
@@ -230,6 +230,6 @@ extern "C" int mcosb_errors(mcosb_ctx* ctx, int S, const double* w, const double
     MCOSB_TRY(st.in(w, (size_t)S * n, SL_STAGE_IN0, &dw));
     MCOSB_TRY(st.in(w_star, w_star_batched ? (size_t)S * n : n, SL_STAGE_IN1, &dws));
     MCOSB_TRY(st.out(err, (size_t)S, SL_STAGE_OUT0, &derr));
-    MCOSB_TRY(mcosb_dev_errors(ctx, S, dw, dws, w_star_batched, kind, derr));
+    MCOSB_TRY(mcosb_dev_errors(ctx, S, dw, dws, w_star_batched, kind, derr, 1));
     return st.finish();
 }

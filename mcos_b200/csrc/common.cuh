@@ -201,5 +201,6 @@ int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* 
 int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* dorder, double* dlink, int* dstatus);
 int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, int max_k, int trials,
                   const int* dlabels_in, double* dw, int* dlabels_out, int* dstatus);
+// derr[s * ld] receives the error of simulation s (ld = 1 for a plain vector, n_optimizers for a column of the table)
 int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int kind,
-                     double* derr);
+                     double* derr, int ld);

@@ -727,11 +727,6 @@ __global__ void __launch_bounds__(VC_THREADS) eigvec_kernel(const double* __rest
     if (status && __syncthreads_or(bad_vec) && tid == 0) atomicOr(&status[s], MCOSB_ST_EIGVEC);
 }
 
-__global__ void zero_int_kernel(int* p, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 0;
-}
-
 int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
                       int* dnf, int* dstatus) {
     if (S == 0) return MCOSB_OK;
@@ -752,10 +747,6 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     if (!lam) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_LAM, (size_t)S * n, &lam));
     nf = dnf;
     if (!nf) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_NF, (size_t)S, &nf));
-    if (dstatus) {
-        zero_int_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(dstatus, (size_t)S);
-        MCOSB_LAUNCHED(ctx);
-    }
     corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
     MCOSB_LAUNCHED(ctx);
 
@@ -796,6 +787,7 @@ extern "C" int mcosb_denoise(mcosb_ctx* ctx, int S, double* cov_inout, int n_obs
     MCOSB_TRY(st.out(var, (size_t)S, SL_STAGE_OUT1, &dvar));
     MCOSB_TRY(st.out(n_facts, (size_t)S, SL_STAGE_OUT2, &dnf));
     MCOSB_TRY(st.out(status, (size_t)S, SL_STAGE_OUT3, &dst));
+    if (dst) MCOSB_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)S * sizeof(int), ctx->stream));
     MCOSB_TRY(mcosb_dev_denoise(ctx, S, dcov, n_obs, bandwidth, deig, dvar, dnf, dst));
     return st.finish();
 }

@@ -288,11 +288,6 @@ __global__ void __launch_bounds__(MK_THREADS) markowitz_kernel(const double* __r
     }
 }
 
-__global__ void zero_int_kernel2(int* p, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 0;
-}
-
 static int mk_fcap(int N) { return N <= 128 ? N : (N <= 600 ? 128 : 192); }
 
 int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, double rf, int clean,
@@ -304,10 +299,6 @@ int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* 
                   ((size_t)fcap + 64) * sizeof(int);
     if (smem > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for markowitz_kernel");
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(markowitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (dstatus) {
-        zero_int_kernel2<<<(S + 255) / 256, 256, 0, ctx->stream>>>(dstatus, (size_t)S);
-        MCOSB_LAUNCHED(ctx);
-    }
     markowitz_kernel<<<S, MK_THREADS, smem, ctx->stream>>>(dmu, dcov, N, fcap, rf, clean, 50 * N + 100, dw, diters,
                                                           dstatus);
     MCOSB_LAUNCHED(ctx);
@@ -328,6 +319,7 @@ extern "C" int mcosb_markowitz(mcosb_ctx* ctx, int S, const double* mu, const do
     MCOSB_TRY(st.out(w, (size_t)S * N, SL_STAGE_OUT0, &dw));
     MCOSB_TRY(st.out(iters, (size_t)S, SL_STAGE_OUT1, &dit));
     MCOSB_TRY(st.out(status, (size_t)S, SL_STAGE_OUT2, &dst));
+    if (dst) MCOSB_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)S * sizeof(int), ctx->stream));
     MCOSB_TRY(mcosb_dev_markowitz(ctx, S, dmu, dcov, rf, clean, dw, dit, dst));
     return st.finish();
 }

@@ -1,0 +1,150 @@
+// mcosb_run: the body of the Monte-Carlo loop (mcos/mcos.py:22-33) for a range of simulation ids, all stages chained on
+// the device, in waves sized to HBM.  The ideal allocation optimizer.allocate(true mu, true cov) (mcos.py:30) is
+// loop-invariant and computed once per call instead of once per simulation.
+#include <algorithm>
+
+#include "common.cuh"
+
+int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W, const double* d_ideal, double* derr,
+                   int* dstatus, std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>& marks) {
+    const size_t N = ctx->N, T = ctx->T;
+    double *dmu, *dcov;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_MUHAT, (size_t)W * N, &dmu));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_COV, (size_t)W * N * N, &dcov));
+    auto mark = [&](int stage, bool begin) -> int {
+        cudaEvent_t e;
+        MCOSB_CUDA(ctx, cudaEventCreate(&e));
+        MCOSB_CUDA(ctx, cudaEventRecord(e, ctx->stream));
+        if (begin) marks.push_back({stage, {e, nullptr}});
+        else marks.back().second.second = e;
+        return MCOSB_OK;
+    };
+    // ---- sampling + moments in sub-chunks so X (8TN bytes per simulation) stays small ---------------------------------
+    const size_t chunk_bytes = (size_t)1 << 30;
+    int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)W, chunk_bytes / (T * N * sizeof(double))));
+    double* dX;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * T * N, &dX));
+    for (int c0 = 0; c0 < W; c0 += CH) {
+        const int nc = std::min(CH, W - c0);
+        MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, true));
+        MCOSB_TRY(mcosb_dev_sample(ctx, sim0 + c0, nc, dX));
+        MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, false));
+        MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, true));
+        MCOSB_TRY(mcosb_dev_moments(ctx, nc, dX, plan->moments_kind, dmu + (size_t)c0 * N, dcov + (size_t)c0 * N * N,
+                                    nullptr));
+        MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, false));
+    }
+    if (plan->denoise) {
+        MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, true));
+        MCOSB_TRY(mcosb_dev_denoise(ctx, W, dcov, ctx->T, plan->bandwidth, nullptr, nullptr, nullptr, dstatus));
+        MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, false));
+    }
+    double* dw;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_RUN_W, (size_t)W * N, &dw));
+    for (int o = 0; o < plan->n_optimizers; ++o) {
+        const int kind = plan->optimizers[o];
+        int stage;
+        if (kind == MCOSB_OPT_MARKOWITZ) {
+            stage = MCOSB_STAGE_MARKOWITZ;
+            MCOSB_TRY(mark(stage, true));
+            MCOSB_TRY(mcosb_dev_markowitz(ctx, W, dmu, dcov, plan->risk_free_rate, 1, dw, nullptr, dstatus));
+        } else if (kind == MCOSB_OPT_HRP) {
+            stage = MCOSB_STAGE_HRP;
+            MCOSB_TRY(mark(stage, true));
+            MCOSB_TRY(mcosb_dev_hrp(ctx, W, dcov, dw, nullptr, nullptr, dstatus));
+        } else {
+            stage = MCOSB_STAGE_NCO;
+            MCOSB_TRY(mark(stage, true));
+            MCOSB_TRY(mcosb_dev_nco(ctx, W, dmu, dcov, plan->nco_max_clusters, plan->nco_trials, nullptr, dw, nullptr,
+                                    dstatus));
+        }
+        MCOSB_TRY(mark(stage, false));
+        MCOSB_TRY(mark(MCOSB_STAGE_ERRORS, true));
+        MCOSB_TRY(mcosb_dev_errors(ctx, W, dw, d_ideal + (size_t)o * N, 0, plan->error_kind, derr + o,
+                                   plan->n_optimizers));
+        MCOSB_TRY(mark(MCOSB_STAGE_ERRORS, false));
+    }
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id0, int S, double* err, int* status) {
+    MCOSB_CHECK_CTX(ctx);
+    if (!plan || S < 0 || !err) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_run");
+    if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
+    if (plan->n_optimizers < 1 || plan->n_optimizers > 4) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_optimizers must be 1..4");
+    for (int o = 0; o < plan->n_optimizers; ++o)
+        if (plan->optimizers[o] < 0 || plan->optimizers[o] > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown optimizer");
+    const size_t N = ctx->N, T = ctx->T;
+    const int nopt = plan->n_optimizers;
+    for (int i = 0; i < MCOSB_N_STAGES; ++i) ctx->stage_ms[i] = 0.0;
+    if (S == 0) return MCOSB_OK;
+
+    Staging st(ctx);
+    double* derr;
+    int* dstatus;
+    MCOSB_TRY(st.out(err, (size_t)S * nopt, SL_ERR, &derr));
+    if (status) MCOSB_TRY(st.out(status, (size_t)S, SL_STATUS, &dstatus));
+    else MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, (size_t)S, &dstatus));
+    MCOSB_CUDA(ctx, cudaMemsetAsync(dstatus, 0, (size_t)S * sizeof(int), ctx->stream));
+
+    // ---- ideal allocations on the true (mu, cov), once ------------------------------------------------------------------
+    double* d_ideal;
+    int* d_ideal_status;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_IDEAL, (size_t)nopt * N + 8, &d_ideal));
+    d_ideal_status = reinterpret_cast<int*>(d_ideal + (size_t)nopt * N);
+    MCOSB_CUDA(ctx, cudaMemsetAsync(d_ideal_status, 0, sizeof(int), ctx->stream));
+    for (int o = 0; o < nopt; ++o) {
+        double* wi = d_ideal + (size_t)o * N;
+        const int kind = plan->optimizers[o];
+        if (kind == MCOSB_OPT_MARKOWITZ)
+            MCOSB_TRY(mcosb_dev_markowitz(ctx, 1, ctx->d_mu, ctx->d_cov, plan->risk_free_rate, 1, wi, nullptr, d_ideal_status));
+        else if (kind == MCOSB_OPT_HRP)
+            MCOSB_TRY(mcosb_dev_hrp(ctx, 1, ctx->d_cov, wi, nullptr, nullptr, d_ideal_status));
+        else
+            MCOSB_TRY(mcosb_dev_nco(ctx, 1, ctx->d_mu, ctx->d_cov, plan->nco_max_clusters, plan->nco_trials, nullptr, wi,
+                                    nullptr, d_ideal_status));
+    }
+
+    // ---- wave size from free HBM -----------------------------------------------------------------------------------------
+    int wave = plan->wave;
+    if (wave <= 0) {
+        size_t free_b = 0, total_b = 0;
+        MCOSB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        size_t held = 0;
+        for (int i = 0; i < SL_COUNT; ++i) held += ctx->slot_bytes[i];
+        // per simulation: cov + denoise work matrix + HRP D and E (4 N^2), inverse-iteration scratch, small vectors
+        size_t per_sim = (4 * N * N + 6 * N * 16 + 16 * N) * sizeof(double);
+        size_t budget = (free_b + held) / 2;
+        size_t fixed = 2 * ((size_t)1 << 30) + ((size_t)1 << 28);  // X + Z chunk buffers
+        size_t w = budget > fixed ? (budget - fixed) / per_sim : 1;
+        wave = (int)std::max<size_t>(1, std::min<size_t>(w, 8192));
+    }
+    wave = std::min(wave, S);
+
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> marks;
+    int rc = MCOSB_OK;
+    for (int s0 = 0; s0 < S && rc == MCOSB_OK; s0 += wave) {
+        const int W = std::min(wave, S - s0);
+        rc = mcosb_run_wave(ctx, plan, sim_id0 + s0, W, d_ideal, derr + (size_t)s0 * nopt, dstatus + s0, marks);
+    }
+    if (rc == MCOSB_OK) rc = st.finish();
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    for (auto& m : marks) {
+        if (m.second.first && m.second.second && se == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, m.second.first, m.second.second) == cudaSuccess) ctx->stage_ms[m.first] += ms;
+        }
+        if (m.second.first) cudaEventDestroy(m.second.first);
+        if (m.second.second) cudaEventDestroy(m.second.second);
+    }
+    if (rc != MCOSB_OK) return rc;
+    if (se != cudaSuccess) return mcosb_fail(ctx, MCOSB_ERR_CUDA, cudaGetErrorString(se));
+    int ideal_status = 0;
+    MCOSB_CUDA(ctx, cudaMemcpy(&ideal_status, d_ideal_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ideal_status) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "ideal allocation on the true (mu, cov) failed with status bits %d", ideal_status);
+        return mcosb_fail(ctx, MCOSB_ERR_STATE, buf);
+    }
+    return MCOSB_OK;
+}

@@ -1,0 +1,77 @@
+"""GPU parity: HRP (K4b-d) through mcosb_hrp.  Bars: cluster order and linkage bit-exact vs scipy, weights 1e-9."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_almost_equal
+
+import oracle
+from conftest import run_cases
+from mcos_b200 import _lib
+from mcos_b200.engine import Engine
+from mcos_b200.synthetic import block_diagonal_truth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(cov, w, info, i):
+    d = oracle.hrp_details(cov)
+    assert np.array_equal(info["order"][i], d["order"])
+    assert np.array_equal(info["linkage"][i], d["linkage"])            # bit-exact, distances included
+    assert_allclose(w[i], d["weights"], rtol=1e-9, atol=1e-15)
+    assert info["status"][i] == 0
+
+
+def test_hrp_golden(stock, literals):
+    """reference tests/test_optimizer.py:55-64 (weights in quasi-diagonal position order)."""
+    eng = Engine(20, 50)
+    w, info = eng.hrp(stock["cov"][None])
+    assert_almost_equal(w[0], literals["hrp_w"])
+    assert list(info["order"][0]) == [15, 12, 4, 17, 19, 9, 14, 7, 10, 11, 13, 0, 5, 16, 8, 18, 1, 6, 2, 3]
+    _check(stock["cov"], w, info, 0)
+
+
+@pytest.mark.parametrize("case", ["stock20_T50", "block100_T200", "block60_T30"])
+def test_hrp_vs_reference_runs(runs, case):
+    keys = run_cases(runs, case)
+    cov = np.stack([runs[f"{k}/denoised"] for k in keys])
+    eng = Engine(cov.shape[1], 10)
+    w, info = eng.hrp(cov)
+    for i, k in enumerate(keys):
+        assert np.array_equal(info["order"][i], runs[f"{k}/hrp_order"])
+        assert np.array_equal(info["linkage"][i], runs[f"{k}/hrp_link"])
+        assert_allclose(w[i], runs[f"{k}/hrp_w"], rtol=1e-9, atol=1e-15)
+
+
+@pytest.mark.parametrize("n,t,nsim", [(500, 1000, 3), (100, 200, 8), (65, 70, 4), (1, 5, 1), (2, 9, 2), (3, 9, 2)])
+def test_hrp_vs_oracle(n, t, nsim):
+    rng = np.random.RandomState(n * 3 + t)
+    if n % 10 == 0:
+        mu, cov = block_diagonal_truth(n)
+    else:
+        a = rng.standard_normal((n, 2 * n + 1))
+        cov = a @ a.T / (2 * n + 1) * 0.01
+        mu = np.zeros(n)
+    covs = np.stack([np.cov(rng.multivariate_normal(mu, cov, size=t), rowvar=False).reshape(n, n) for _ in range(nsim)])
+    eng = Engine(n, t)
+    w, info = eng.hrp(covs)
+    for i in range(nsim):
+        if n == 1:
+            assert w[i, 0] == 1.0
+        else:
+            _check(covs[i], w, info, i)
+
+
+def test_hrp_exact_ties():
+    """The true block-diagonal covariance has massive exact ties in every distance: the merge order then depends on
+    Prim's lowest-index rule and the stable sort, which must match scipy's."""
+    for n, blocks in ((20, 2), (60, 6), (100, 10)):
+        mu, cov = block_diagonal_truth(n, n_blocks=blocks)
+        eng = Engine(n, 10)
+        w, info = eng.hrp(cov[None])
+        _check(cov, w, info, 0)
+    # rounded inputs -> ties in the sample covariance too
+    rng = np.random.RandomState(0)
+    x = np.round(rng.standard_normal((50, 30)), 1)
+    cov = np.cov(x, rowvar=False)
+    eng = Engine(30, 50)
+    w, info = eng.hrp(cov[None])
+    _check(cov, w, info, 0)
