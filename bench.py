@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the MCOS Monte-Carlo loop on B200 (BASELINE.json metric: Monte-Carlo simulations per second at
+N=500, T=1000, Ledoit-Wolf + DeNoiser, Markowitz + HRP, Sharpe error).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this engine
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                     # one rank per GPU, simulations sharded by id
+    python bench.py --impl reference --gpus 1 --steps K --warmup W # the reference's CPU path (oracle port) on host cores
+
+A "step" is one pass of the whole loop body (sample -> moments -> de-noise -> Markowitz + HRP -> errors) over a batch of
+`--sims-per-step` simulations per GPU; the 100 000-simulation job of BASELINE config 3 is ceil(1e5 / batch) such steps
+and its throughput in simulations/s is the same number.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ASSETS, N_OBS = 500, 1000
+WORKLOAD = "BASELINE config 3: synthetic block-diagonal truth N=500 (10 blocks x 50, rho=0.5), T=1000, " \
+           "MuCovLedoitWolf + DeNoiser(0.25), Markowitz + HRP, SharpeRatioErrorEstimator"
+
+
+def load_peaks():
+    """Roofline denominators: HBM from the driver-written MEASURED_PEAKS.json (fallback 6650 GB/s), FP64 from this
+    repo's own measurement on the same pool (profiles/fp64_peaks_r01.json; MEASURED_PEAKS.json has no FP64 entry)."""
+    hbm, src = 6650.0, "fallback"
+    try:
+        hbm, src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    fp64 = {"dfma_tflops": 36.7, "dmma_tflops": 37.0, "dmul_dadd_tinstr": 18.28}
+    try:
+        raw = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))
+        fp64 = {"dfma_tflops": raw["dfma_tflops_b2_t1024"], "dmma_tflops": raw["dmma1688_tflops_b2_t512"],
+                "dmul_dadd_tinstr": raw["dmul_dadd_tinstr"]}
+    except Exception:
+        pass
+    return hbm, src, fp64
+
+
+def kernel_models(n, t):
+    """Algorithmic work per simulation of each kernel: (bound, work per simulation, unit)."""
+    n3 = float(n) ** 3
+    return {
+        "philox_normal": ("hbm", 8.0 * t * n, "B"),                       # writes Z once
+        "trmm": ("tensor", 2.0 * t * n * n / 2, "flop"),                  # triangular Z L'
+        "colmean": ("hbm", 8.0 * t * n, "B"),
+        "syrk": ("tensor", 2.0 * t * n * n / 2, "flop"),                  # lower triangle of Xc'Xc
+        "lw_rownorm": ("hbm", 8.0 * t * n, "B"),
+        "lw_finish": ("hbm", 16.0 * n * n, "B"),
+        "corr": ("hbm", 16.0 * n * n, "B"),
+        "tridiag": ("fp64", 4.0 * n3 / 3, "flop"),                        # Householder tridiagonalisation
+        "eigvals": ("fp64", 2.0 * 2 * 64 * n * n, "flop"),                # 64 bisection steps x N-step Sturm recurrence
+        "mpfit": ("fp64", 11 * 1000.0 * n * 25, "flop"),                  # ~11 objective passes x 1000 x N exp (~25 flop)
+        "eigvec": ("hbm", 3 * 8.0 * n * n, "B"),                          # reflectors read + cov written and rescaled
+        "markowitz": ("hbm", 8.0 * n * 50 * 60, "B"),                     # ~60 iterations x |F|~50 rows of C from L2
+        "hrp_dist": ("hbm", 16.0 * n * n, "B"),
+        "hrp_euclid": ("fp64_nofma", 3.0 * n3 / 2, "instr"),              # sub, mul, add per (i<j, k): bit-exact, no FMA
+        "hrp_tree": ("hbm", 8.0 * n * n + 16.0 * n * n, "B"),            # E rows once + gathered cov for the bisection
+        "errors": ("hbm", 8.0 * n * n / 8, "B"),                          # true cov shared by 8 simulations per CTA
+    }
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = sorted(x for x in sm if mx is None or x > 0.3 * mx) or sorted(sm)
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference loop on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(seed):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import oracle
+    from mcos_b200.synthetic import block_diagonal_truth
+    mu, cov = block_diagonal_truth(N_ASSETS)
+    np.random.seed(seed)
+    t0 = time.time()
+    oracle.simulate_optimizations(mu, cov, N_OBS, 1, simulator="mucovledoitwolf", transformers=[("denoise", 0.25)],
+                                  optimizers=("markowitz", "HRP"), estimator="sharpe")
+    return time.time() - t0
+
+
+def cpu_reference_pass(cores, seed0):
+    """One bounded sample: `cores` simulations of the headline workload, one per worker process with BLAS threads
+    pinned to 1 (the reference itself is single-threaded Python). Returns (simulations, wall seconds)."""
+    import multiprocessing as mp
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"
+    try:
+        ctx = mp.get_context("spawn")
+        t0 = time.time()
+        with ctx.Pool(cores) as pool:
+            pool.map(_cpu_worker, [seed0 + i for i in range(cores)])
+        return cores, time.time() - t0
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1))
+    budget = float(os.environ.get("MCOSB_REF_BUDGET_S", "420"))
+    t_start = time.time()
+    # every pass costs about one reference simulation per core (~1 min at N=500: two SLSQP solves of ~25 s each), so
+    # the W + K passes are cut short when the next one would overrun the time budget; the LAST min(K, done) passes are
+    # the timed ones, whatever ran before them is warm-up
+    passes = []
+    for i in range(args.warmup + args.steps):
+        elapsed = time.time() - t_start
+        if passes and elapsed + elapsed / len(passes) > budget:
+            break
+        passes.append(cpu_reference_pass(cores, 1000 * i))
+    timed = passes[-min(args.steps, len(passes)):]
+    done_warm = len(passes) - len(timed)
+    times = [dt for _, dt in timed]
+    sims = sum(n for n, _ in timed)
+    total = sum(times)
+    value = sims / total
+    sample = f"{cores} simulations per step (one per worker process, BLAS threads = 1), {len(times)} timed step(s), " \
+             f"{done_warm} warm-up step(s); time budget {budget:.0f} s"
+    line = {
+        "impl": "reference", "metric": "Monte Carlo sims/sec (N=500,T=1000, DeNoise+Markowitz+HRP)", "value": value,
+        "unit": "sims/s", "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps,
+        "warmup": done_warm, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_assets": N_ASSETS, "n_observations": N_OBS, "sims_per_step": cores,
+                   "note": "oracle port of mcos/mcos.py:22-33 (numpy/scipy/sklearn + PyPortfolioOpt-0.5.2-semantics "
+                           "SLSQP), ideal allocation recomputed per simulation as the reference does"},
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from mcos_b200 import _lib
+    import mcos_b200 as mb
+    from mcos_b200.engine import get_engine
+    from mcos_b200.synthetic import block_diagonal_truth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    spp = args.sims_per_step
+    mu, cov = block_diagonal_truth(N_ASSETS)
+    sim = mb.MuCovLedoitWolfObservationSimulator(mu, cov, N_OBS, seed=args.seed, device=local)
+    optimizers = [mb.MarkowitzOptimizer(), mb.HRPOptimizer()]
+    estimator = mb.SharpeRatioErrorEstimator()
+    transformers = [mb.DeNoiserCovarianceTransformer()]
+    plan = mb.build_plan(sim, optimizers, estimator, transformers)
+    eng = get_engine(N_ASSETS, N_OBS, local, args.seed)
+    eng.ensure_truth(mu, cov)          # inputs resident in HBM before the timed region
+    eng.use_torch_stream()
+
+    def step(i, out_torch=True):
+        # rank r, step i works on its own contiguous block of simulation ids (weak scaling, no data-path collective)
+        sim0 = (i * world + rank) * spp
+        return eng.run(plan, spp, sim0, out_torch=out_torch)
+
+    for i in range(args.warmup):
+        step(i)
+    eng.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    status_bad = 0
+    for i in range(args.steps):
+        err, st = step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ktimes = eng.kernel_times()
+    stage_ms = eng.last_stage_ms()
+    eng.set_profiling(False)
+    status_bad = int((st != 0).sum().item())
+    nan_frac = float(torch.isnan(err).float().mean().item())
+
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * spp * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with host buffers (truth re-uploaded from pinned memory every step) --------
+    e2e = None
+    if not args.no_e2e:
+        pin_mu = torch.empty(N_ASSETS, dtype=torch.float64).pin_memory()
+        pin_cov = torch.empty((N_ASSETS, N_ASSETS), dtype=torch.float64).pin_memory()
+        pin_mu.copy_(torch.from_numpy(mu)); pin_cov.copy_(torch.from_numpy(cov))
+        sim_h = mb.MuCovLedoitWolfObservationSimulator(pin_mu.numpy(), pin_cov.numpy(), N_OBS, seed=args.seed, device=local)
+
+        def e2e_step(i):
+            eng.mu = None        # forget the resident truth: this step uploads (mu, cov) again and refactors it
+            errors, _ = mb.simulate_errors(sim_h, spp * world, optimizers, estimator, transformers, device=local,
+                                           sim_id0=i * world * spp)
+            return errors        # host numpy [world * spp, 2], gathered over ranks in simulation-id order
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            errors = e2e_step(1 + i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * spp * args.steps / float(dt.item()), "unit": "sims/s",
+               "h2d_bytes_per_step": 8 * (N_ASSETS + N_ASSETS * N_ASSETS),
+               "d2h_bytes_per_step": spp * (2 * 8 + 4),
+               "api": "mcos_b200.simulate_errors (host numpy in/out; pinned truth uploaded every step)"}
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------------------
+    hbm, hbm_src, fp64 = load_peaks()
+    models = kernel_models(N_ASSETS, N_OBS)
+    sims_timed = spp * args.steps
+    table = {}
+    for name, (ms, cnt) in ktimes.items():
+        if not cnt or name not in models:
+            continue
+        bound, work, unit = models[name]
+        rate = work * sims_timed / (ms * 1e-3)
+        if bound == "hbm":
+            ach, peak, u = rate / 1e9, hbm, "GB/s"
+        elif bound == "tensor":
+            ach, peak, u = rate / 1e12, fp64["dmma_tflops"], "TFLOP/s"
+        elif bound == "fp64":
+            ach, peak, u = rate / 1e12, fp64["dfma_tflops"], "TFLOP/s"
+        else:
+            ach, peak, u = rate / 1e12, fp64["dmul_dadd_tinstr"], "Tinstr/s"
+        table[name] = {"ms": round(ms, 3), "launches": cnt, "share": None, "bound": bound, "achieved": ach, "peak": peak,
+                       "unit": u, "frac": ach / peak}
+    tot = sum(v["ms"] for v in table.values()) or 1.0
+    for v in table.values():
+        v["share"] = round(v["ms"] / tot, 4)
+    top = max(table, key=lambda k: table[k]["ms"])
+    tv = table[top]
+    roofline = {"kernel": top + "_kernel", "bound": tv["bound"] if tv["bound"] in ("hbm", "tensor") else "fp64",
+                "achieved": tv["achieved"], "peak": tv["peak"], "unit": tv["unit"], "frac": tv["frac"], "traffic": None,
+                "share_of_step": tv["share"], "ms_per_launch": tv["ms"] / tv["launches"],
+                "peak_source": ("MEASURED_PEAKS.json (%s)" % hbm_src) if tv["bound"] == "hbm"
+                else "profiles/fp64_peaks_r01.json (measured on this pool; MEASURED_PEAKS.json has no FP64 entry)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = min(os.cpu_count() or 1, args.cpu_cores or (os.cpu_count() or 1))
+        try:
+            n, dt = cpu_reference_pass(cores, 12345)
+            cpu_baseline = {"value": n / dt, "unit": "sims/s", "cores": cores, "kind": "port",
+                            "sample": f"{n} simulations of the same workload, one per worker process (BLAS threads = 1), "
+                                      f"{dt:.1f} s wall"}
+        except Exception as exc:  # pragma: no cover
+            cpu_baseline = {"value": None, "unit": "sims/s", "cores": cores, "kind": "port", "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": "Monte Carlo sims/sec (N=500,T=1000, DeNoise+Markowitz+HRP)", "value": value, "unit": "sims/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_assets": N_ASSETS, "n_observations": N_OBS, "sims_per_step_per_gpu": spp,
+                       "job_100k_sims_steps": -(-100000 // (spp * world)), "parallelism": f"sim-id sharding x{world}",
+                       "l2": "working set per step (>= 4 N^2 x 8 B x sims = %.1f GB) is far larger than the 126 MB L2; "
+                             "no flush needed" % (4 * N_ASSETS * N_ASSETS * 8 * spp / 1e9),
+                       "seed": args.seed},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "stage_ms_last_step": {k: round(v, 3) for k, v in stage_ms.items()},
+            "kernels": table, "status_nonzero_last_step": status_bad, "nan_fraction_last_step": nan_frac,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--sims-per-step", type=int, default=2048)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

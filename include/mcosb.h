@@ -133,6 +133,14 @@ int mcosb_last_stage_ms(mcosb_ctx* ctx, double* stage_ms);
 /* Number of kernel launches issued by this context since creation. */
 long long mcosb_launch_count(const mcosb_ctx* ctx);
 
+/* Per-kernel device time.  mcosb_set_profiling(ctx, 1) resets the counters and makes every launch record a CUDA
+ * event on the context's stream; mcosb_kernel_times() synchronizes and fills ms[k] / launches[k] for
+ * k < mcosb_kernel_count(), named by mcosb_kernel_name(k). */
+int mcosb_set_profiling(mcosb_ctx* ctx, int on);
+int mcosb_kernel_count(void);
+const char* mcosb_kernel_name(int id);
+int mcosb_kernel_times(mcosb_ctx* ctx, double* ms, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

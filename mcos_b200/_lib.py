@@ -48,6 +48,10 @@ SIGNATURES = {
     "mcosb_run": (c_int, [c_void_p, POINTER(Plan), c_uint64, c_int, c_void_p, c_void_p]),
     "mcosb_last_stage_ms": (c_int, [c_void_p, POINTER(c_double)]),
     "mcosb_launch_count": (c_longlong, [c_void_p]),
+    "mcosb_set_profiling": (c_int, [c_void_p, c_int]),
+    "mcosb_kernel_count": (c_int, []),
+    "mcosb_kernel_name": (c_char_p, [c_int]),
+    "mcosb_kernel_times": (c_int, [c_void_p, POINTER(c_double), POINTER(c_longlong)]),
 }
 
 _lib = None

@@ -114,7 +114,7 @@ extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* c
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, 1, &dflag));
     MCOSB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
     chol_truth_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_chol, ctx->N, dflag);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
     int flag = 0;
     MCOSB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -215,7 +215,7 @@ int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwst
     int grid = (S + ERR_SB - 1) / ERR_SB;
     errors_kernel<<<grid, ERR_THREADS, smem, ctx->stream>>>(dw, dwstar, batched, ctx->d_mu, ctx->d_cov, ctx->N, S,
                                                            kind, derr, ld);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_ERRORS);
     return MCOSB_OK;
 }
 
@@ -232,4 +232,45 @@ extern "C" int mcosb_errors(mcosb_ctx* ctx, int S, const double* w, const double
     MCOSB_TRY(st.out(err, (size_t)S, SL_STAGE_OUT0, &derr));
     MCOSB_TRY(mcosb_dev_errors(ctx, S, dw, dws, w_star_batched, kind, derr, 1));
     return st.finish();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-kernel timing: with profiling on, every launch is followed by an event on the context's stream; a kernel's
+// duration is the gap between its event and the previous one.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mcosb_set_profiling(mcosb_ctx* ctx, int on) {
+    MCOSB_CHECK_CTX(ctx);
+    MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& k : ctx->kev) cudaEventDestroy(k.second);
+    ctx->kev.clear();
+    for (int i = 0; i < MK_COUNT; ++i) { ctx->kernel_ms[i] = 0.0; ctx->kernel_launches[i] = 0; }
+    ctx->profile = on != 0;
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_kernel_count(void) { return MK_COUNT; }
+
+extern "C" const char* mcosb_kernel_name(int id) { return (id >= 0 && id < MK_COUNT) ? MCOSB_KERNEL_NAMES[id] : ""; }
+
+extern "C" int mcosb_kernel_times(mcosb_ctx* ctx, double* ms, long long* launches) {
+    MCOSB_CHECK_CTX(ctx);
+    MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 1; i < ctx->kev.size(); ++i) {
+        if (ctx->kev[i].first < 0) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->kev[i - 1].second, ctx->kev[i].second) == cudaSuccess)
+            ctx->kernel_ms[ctx->kev[i].first] += t;
+    }
+    if (!ctx->kev.empty()) {  // keep the last event as the anchor for what follows
+        for (size_t i = 0; i + 1 < ctx->kev.size(); ++i) cudaEventDestroy(ctx->kev[i].second);
+        auto last = ctx->kev.back();
+        last.first = -1;
+        ctx->kev.clear();
+        ctx->kev.push_back(last);
+    }
+    for (int i = 0; i < MK_COUNT; ++i) {
+        if (ms) ms[i] = ctx->kernel_ms[i];
+        if (launches) launches[i] = ctx->kernel_launches[i];
+    }
+    return MCOSB_OK;
 }

@@ -23,6 +23,48 @@ enum ScratchSlot {
     SL_COUNT
 };
 
+enum KernelId {
+    MK_CHOL_TRUTH,
+    MK_ERRORS,
+    MK_COLMEAN,
+    MK_SYRK,
+    MK_LW_ROWNORM,
+    MK_LW_FINISH,
+    MK_FILL,
+    MK_PHILOX_NORMAL,
+    MK_TRMM,
+    MK_CORR,
+    MK_TRIDIAG,
+    MK_EIGVALS,
+    MK_MPFIT,
+    MK_EIGVEC,
+    MK_MARKOWITZ,
+    MK_HRP_DIST,
+    MK_HRP_EUCLID,
+    MK_HRP_TREE,
+    MK_COUNT
+};
+static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
+    "chol_truth",
+    "errors",
+    "colmean",
+    "syrk",
+    "lw_rownorm",
+    "lw_finish",
+    "fill",
+    "philox_normal",
+    "trmm",
+    "corr",
+    "tridiag",
+    "eigvals",
+    "mpfit",
+    "eigvec",
+    "markowitz",
+    "hrp_dist",
+    "hrp_euclid",
+    "hrp_tree"
+};
+
 struct mcosb_ctx {
     int device = 0;
     int N = 0, T = 0;
@@ -40,6 +82,12 @@ struct mcosb_ctx {
     double stage_ms[MCOSB_N_STAGES] = {};
     int smem_optin = 0;
     int num_sms = MCOSB_SMS;
+    // per-kernel timing (mcosb_set_profiling): one event after every launch; a kernel's time is the gap to the
+    // previous event on the stream
+    bool profile = false;
+    std::vector<std::pair<int, cudaEvent_t>> kev;
+    double kernel_ms[MK_COUNT] = {};
+    long long kernel_launches[MK_COUNT] = {};
 };
 
 inline int mcosb_fail(mcosb_ctx* ctx, int code, const std::string& msg) {
@@ -65,10 +113,28 @@ inline int mcosb_fail(mcosb_ctx* ctx, int code, const std::string& msg) {
     } while (0)
 
 // After every kernel launch: count it and surface launch-configuration errors immediately.
-#define MCOSB_LAUNCHED(ctx)                      \
-    do {                                         \
-        (ctx)->launches++;                       \
-        MCOSB_CUDA(ctx, cudaGetLastError());     \
+#define MCOSB_LAUNCHED(ctx, kid)                                        \
+    do {                                                                \
+        (ctx)->launches++;                                              \
+        (ctx)->kernel_launches[kid]++;                                  \
+        MCOSB_CUDA(ctx, cudaGetLastError());                            \
+        if ((ctx)->profile) {                                           \
+            cudaEvent_t ev__;                                            \
+            MCOSB_CUDA(ctx, cudaEventCreate(&ev__));                     \
+            MCOSB_CUDA(ctx, cudaEventRecord(ev__, (ctx)->stream));       \
+            (ctx)->kev.push_back({kid, ev__});                           \
+        }                                                               \
+    } while (0)
+
+// Marks a point on the stream that is not a kernel (start of a wave, after a copy) so the next kernel's gap is clean.
+#define MCOSB_PROFILE_MARK(ctx)                                         \
+    do {                                                                \
+        if ((ctx)->profile) {                                           \
+            cudaEvent_t ev__;                                            \
+            MCOSB_CUDA(ctx, cudaEventCreate(&ev__));                     \
+            MCOSB_CUDA(ctx, cudaEventRecord(ev__, (ctx)->stream));       \
+            (ctx)->kev.push_back({-1, ev__});                            \
+        }                                                               \
     } while (0)
 
 // Grow-only device scratch, one buffer per slot.

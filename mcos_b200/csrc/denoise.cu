@@ -748,29 +748,29 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     nf = dnf;
     if (!nf) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_NF, (size_t)S, &nf));
     corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_CORR);
 
     size_t smem_td = (4 * n + TD_WARPS * 32) * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_td));
     tridiag_kernel<<<S, TD_THREADS, smem_td, ctx->stream>>>(A, N, d, e, tau);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_TRIDIAG);
 
     size_t smem_ev = 2 * n * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ev));
     eigvals_kernel<<<S, EV_THREADS, smem_ev, ctx->stream>>>(d, e, N, lam);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_EIGVALS);
 
     const double q = (double)n_obs / (double)N;
     size_t smem_mp = n * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(mpfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mp));
     mpfit_kernel<<<S, MP_THREADS, smem_mp, ctx->stream>>>(lam, N, q, bandwidth, dvar, nf, dstatus);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_MPFIT);
 
     size_t smem_vc = (2 * n + (size_t)VC_VCH * n + VC_VCH) * sizeof(double);
     if (smem_vc > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for eigvec_kernel");
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vc));
     eigvec_kernel<<<S, VC_THREADS, smem_vc, ctx->stream>>>(A, N, d, e, tau, lam, nf, sigma, work, piv, dcov, dstatus);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_EIGVEC);
     return MCOSB_OK;
 }
 

@@ -301,15 +301,15 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_WORK, (size_t)S * n * n, &D));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_E, (size_t)S * n * n, &E));
     hrp_dist_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, D);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_HRP_DIST);
     const int nt = (N + EU_T - 1) / EU_T;
     hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, N, E);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
     size_t smem = (3 * n + 32) * sizeof(double) + (4 * n + 4 * n + n + 2 * (n + 1) + n + 32) * sizeof(int);
     if (smem > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for hrp_tree_kernel");
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hrp_tree_kernel<<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, dorder, dlink, dstatus);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_HRP_TREE);
     return MCOSB_OK;
 }
 

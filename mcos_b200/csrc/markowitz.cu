@@ -301,7 +301,7 @@ int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* 
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(markowitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     markowitz_kernel<<<S, MK_THREADS, smem, ctx->stream>>>(dmu, dcov, N, fcap, rf, clean, 50 * N + 100, dw, diters,
                                                           dstatus);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_MARKOWITZ);
     return MCOSB_OK;
 }
 

@@ -211,7 +211,7 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
 
     dim3 gm((N + CM_COLS - 1) / CM_COLS, S);
     colmean_kernel<<<gm, CM_COLS * CM_ROWGROUPS, 0, ctx->stream>>>(dX, T, N, dmu);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_COLMEAN);
 
     const int nt = (N + DM_BM - 1) / DM_BM, ntiles = nt * (nt + 1) / 2;
     double* lwpart = nullptr;
@@ -220,19 +220,19 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double scale = lw ? 1.0 / T : 1.0 / (T - 1);
     syrk_kernel<<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_SYRK);
 
     if (lw) {
         const int nchunks = (T + RN_ROWS - 1) / RN_ROWS;
         double* rnpart = nullptr;
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWSTAT, (size_t)S * nchunks, &rnpart));
         lw_rownorm_kernel<<<dim3(nchunks, S), 256, 0, ctx->stream>>>(dX, dmu, T, N, rnpart);
-        MCOSB_LAUNCHED(ctx);
+        MCOSB_LAUNCHED(ctx, MK_LW_ROWNORM);
         lw_finish_kernel<<<S, 256, 0, ctx->stream>>>(dcov, lwpart, ntiles, rnpart, nchunks, T, N, dshrink);
-        MCOSB_LAUNCHED(ctx);
+        MCOSB_LAUNCHED(ctx, MK_LW_FINISH);
     } else if (dshrink) {
         fill_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(dshrink, (size_t)S, 0.0);
-        MCOSB_LAUNCHED(ctx);
+        MCOSB_LAUNCHED(ctx, MK_FILL);
     }
     return MCOSB_OK;
 }

@@ -19,6 +19,7 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
         else marks.back().second.second = e;
         return MCOSB_OK;
     };
+    MCOSB_PROFILE_MARK(ctx);
     // ---- sampling + moments in sub-chunks so X (8TN bytes per simulation) stays small ---------------------------------
     const size_t chunk_bytes = (size_t)1 << 30;
     int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)W, chunk_bytes / (T * N * sizeof(double))));
@@ -87,6 +88,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     else MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, (size_t)S, &dstatus));
     MCOSB_CUDA(ctx, cudaMemsetAsync(dstatus, 0, (size_t)S * sizeof(int), ctx->stream));
 
+    MCOSB_PROFILE_MARK(ctx);
     // ---- ideal allocations on the true (mu, cov), once ------------------------------------------------------------------
     double* d_ideal;
     int* d_ideal_status;

@@ -131,14 +131,14 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     size_t pairs = M * ((N + 1) / 2);
     int grid = (int)std::min<size_t>((pairs + 255) / 256, (size_t)ctx->num_sms * 16);
     philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
     const size_t smem = (size_t)4 * DM_BM * DM_LD_MMAJOR * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t row_tiles = (M + DM_BM - 1) / DM_BM;
     if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");
     dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
     trmm_kernel<<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
-    MCOSB_LAUNCHED(ctx);
+    MCOSB_LAUNCHED(ctx, MK_TRMM);
     return MCOSB_OK;
 }
 

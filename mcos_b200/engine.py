@@ -32,6 +32,7 @@ class Engine:
             raise MCOSBError(f"mcosb_create failed with code {rc}: a CUDA device is required (no CPU fallback)")
         self.h = handle
         self.mu = self.cov = None
+        self.truth_pd = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -86,13 +87,36 @@ class Engine:
         self._check(self.lib.mcosb_last_stage_ms(self.h, buf))
         return dict(zip(_lib.STAGE_NAMES, list(buf)))
 
+    def set_profiling(self, on=True):
+        self._check(self.lib.mcosb_set_profiling(self.h, int(bool(on))))
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} since set_profiling(True)."""
+        n = self.lib.mcosb_kernel_count()
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_longlong * n)()
+        self._check(self.lib.mcosb_kernel_times(self.h, ms, cnt))
+        return {self.lib.mcosb_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}
+
     # ---- stages --------------------------------------------------------------------------------------------------
-    def set_truth(self, mu, cov):
+    def set_truth(self, mu, cov, require_pd=True):
+        """Uploads the true (mu, cov). With require_pd=False a covariance that has no Cholesky factor is accepted
+        (the error estimators only need mu and cov themselves); sampling from it would still fail."""
         mu_a = np.ascontiguousarray(np.asarray(mu, dtype=np.float64).reshape(self.N))
         cov_a = np.ascontiguousarray(np.asarray(cov, dtype=np.float64).reshape(self.N, self.N))
+        if self.mu is not None and np.array_equal(mu_a, self.mu) and np.array_equal(cov_a, self.cov) and \
+                (self.truth_pd or not require_pd):
+            return
         self.mu, self.cov = mu_a, cov_a
-        self._check(self.lib.mcosb_set_truth(self.h, mu_a.ctypes.data_as(ctypes.c_void_p),
-                                             cov_a.ctypes.data_as(ctypes.c_void_p)))
+        rc = self.lib.mcosb_set_truth(self.h, mu_a.ctypes.data_as(ctypes.c_void_p),
+                                      cov_a.ctypes.data_as(ctypes.c_void_p))
+        self.truth_pd = rc == 0
+        if rc == -4 and not require_pd:
+            return
+        self._check(rc)
+
+    def ensure_truth(self, mu, cov):
+        self.set_truth(mu, cov, require_pd=True)
 
     def sample(self, n_sims, sim_id0=0, out_torch=False):
         x, px = self._out(out_torch, (n_sims, self.T, self.N))
