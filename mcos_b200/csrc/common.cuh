@@ -42,6 +42,9 @@ enum KernelId {
     MK_HRP_DIST,
     MK_HRP_EUCLID,
     MK_HRP_TREE,
+    MK_NCO_DIST,
+    MK_NCO_CLUSTER,
+    MK_NCO_ALLOC,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -62,7 +65,10 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "markowitz",
     "hrp_dist",
     "hrp_euclid",
-    "hrp_tree"
+    "hrp_tree",
+    "nco_dist",
+    "nco_cluster",
+    "nco_alloc"
 };
 
 struct mcosb_ctx {

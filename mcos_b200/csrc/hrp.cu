@@ -293,6 +293,12 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
     if (tid == 0 && status && !(tot <= 1.001 && tot >= 0.999)) atomicOr(&status[s], MCOSB_ST_HRP_SUM);
 }
 
+// Euclidean distances between the rows of D for S matrices (also used by NCO's silhouettes); the caller accounts for it.
+void mcosb_launch_euclid(mcosb_ctx* ctx, int S, const double* D, double* E) {
+    const int nt = (ctx->N + EU_T - 1) / EU_T;
+    hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, ctx->N, E);
+}
+
 int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* dorder, double* dlink, int* dstatus) {
     if (S == 0) return MCOSB_OK;
     const int N = ctx->N;
