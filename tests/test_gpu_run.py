@@ -110,7 +110,7 @@ def test_plugin_methods_single_inputs(stock, literals):
     a, o = literals["est_allocation"], literals["est_optimal_allocation"]
     for est, want in zip((mb.ExpectedOutcomeErrorEstimator(), mb.VarianceErrorEstimator(), mb.SharpeRatioErrorEstimator()),
                          literals["est_expected"]):
-        assert abs(est.estimate(mu, cov, a, o) - want) < 5e-8
+        assert abs(est.estimate(mu, cov, a, o) - want) < 1.5e-7   # assert_almost_equal(decimal=7), as the reference
     assert mb.MarkowitzOptimizer().name == "markowitz" and mb.HRPOptimizer().name == "HRP" and mb.NCOOptimizer().name == "NCO"
     mh, ch = mb.MuCovObservationSimulator(mu, cov, 50).simulate()
     assert mh.shape == (20, 1) and ch.shape == (20, 20)
