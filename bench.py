@@ -59,6 +59,7 @@ def kernel_models(n, t):
         "lw_finish": ("hbm", 16.0 * n * n, "B"),
         "corr": ("hbm", 16.0 * n * n, "B"),
         "tridiag": ("fp64", 4.0 * n3 / 3, "flop"),                        # Householder tridiagonalisation
+        "tridiag2": ("fp64", 4.0 * n3 / 3, "flop"),                       # blocked, lower triangle only
         "eigvals": ("fp64", 2.0 * 2 * 64 * n * n, "flop"),                # 64 bisection steps x N-step Sturm recurrence
         "mpfit": ("fp64", 11 * 1000.0 * n * 25, "flop"),                  # ~11 objective passes x 1000 x N exp (~25 flop)
         "eigvec": ("hbm", 3 * 8.0 * n * n, "B"),                          # reflectors read + cov written and rescaled

@@ -45,6 +45,7 @@ enum KernelId {
     MK_NCO_DIST,
     MK_NCO_CLUSTER,
     MK_NCO_ALLOC,
+    MK_TRIDIAG2,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -68,7 +69,8 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "hrp_tree",
     "nco_dist",
     "nco_cluster",
-    "nco_alloc"
+    "nco_alloc",
+    "tridiag2"
 };
 
 struct mcosb_ctx {

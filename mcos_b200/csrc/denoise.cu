@@ -12,6 +12,8 @@
 // reconstruction needs are ever formed:  V L' V' = lbar I + V_s (L_s - lbar I) V_s'  because V V' = I.
 #include "common.cuh"
 
+int mcosb_launch_tridiag2(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau);
+
 // ---------------------------------------------------------------------------------------------------------------
 // D1: correlation matrix.  grid = (ceil(N/8), S), 256 threads, one warp per row.
 // ---------------------------------------------------------------------------------------------------------------
@@ -750,10 +752,16 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
     MCOSB_LAUNCHED(ctx, MK_CORR);
 
-    size_t smem_td = (4 * n + TD_WARPS * 32) * sizeof(double);
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_td));
-    tridiag_kernel<<<S, TD_THREADS, smem_td, ctx->stream>>>(A, N, d, e, tau);
-    MCOSB_LAUNCHED(ctx, MK_TRIDIAG);
+    int r2 = mcosb_launch_tridiag2(ctx, S, A, d, e, tau);  // blocked, lower triangle only (tridiag2.cu)
+    if (r2 < 0) return r2;
+    if (r2 == 1) {
+        MCOSB_LAUNCHED(ctx, MK_TRIDIAG2);
+    } else {
+        size_t smem_td = (4 * n + TD_WARPS * 32) * sizeof(double);
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_td));
+        tridiag_kernel<<<S, TD_THREADS, smem_td, ctx->stream>>>(A, N, d, e, tau);
+        MCOSB_LAUNCHED(ctx, MK_TRIDIAG);
+    }
 
     size_t smem_ev = 2 * n * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ev));
