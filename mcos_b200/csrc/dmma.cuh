@@ -3,11 +3,14 @@
 // tcgen05 has no f64 kind, so the FP64 tensor path on sm_100a is the warp-level mma.sync m8n8k4 (SASS DMMA.8x8x4;
 // measured 37.0 TFLOP/s on B200, profiles/fp64_peaks_r01.json).  A CTA of 256 threads (8 warps as 2 x 4) owns a
 // 128 x 128 FP64 accumulator tile; each warp owns 64 x 32 of it as 8 x 4 m8n8 blocks = 64 doubles per thread.
+// Operand tiles move global -> shared with cp.async (LDGSTS, 8-byte, zero-fill for the ragged edges) through a
+// DM_STAGES-deep ring, one __syncthreads per k-slab.
 #pragma once
 
 #define DM_BM 128
 #define DM_BN 128
 #define DM_BK 16
+#define DM_STAGES 3
 #define DM_THREADS 256
 #define DM_WM 64   // warp tile rows
 #define DM_WN 32   // warp tile cols
@@ -16,6 +19,8 @@
 // shared-memory leading dimensions (doubles); both keep a half-warp's 16 fragment loads on 16 distinct bank pairs
 #define DM_LD_KMAJOR (DM_BM + 4)  // tile stored [k][m]
 #define DM_LD_MMAJOR (DM_BK + 4)  // tile stored [m][k]
+#define DM_TILE_KMAJOR (DM_BK * DM_LD_KMAJOR)
+#define DM_TILE_MMAJOR (DM_BM * DM_LD_MMAJOR)
 
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -23,24 +28,42 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                  : "d"(a), "d"(b));
 }
 
+// 8-byte asynchronous copy global -> shared; copies nothing and zero-fills when !pred (src must still be a valid address)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool pred) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
 // One BK-deep slab of MMAs for this warp.  KMAJOR: tile element (mn, k) lives at tile[k * ld + mn]; otherwise at
 // tile[mn * ld + k].  acc[mb][nb][2] follows the m8n8k4 C layout: row = lane/4, cols = 2*(lane%4) + {0,1}.
-template <bool A_KMAJOR, bool B_KMAJOR>
+// CENTER: subtract per-column offsets (amean[mb], bmean[nb]) from the fragments as they are loaded -- the SYRK's
+// centring x - mean, done in registers so the tiles can be copied raw; only the first kvalid k-rows of the slab count
+// (rows beyond hold zero fill and must contribute nothing).
+template <bool A_KMAJOR, bool B_KMAJOR, bool CENTER>
 __device__ __forceinline__ void dmma_slab(const double* __restrict__ As, const double* __restrict__ Bs, int wm0,
-                                          int wn0, int lane, double (&acc)[DM_MB][DM_NB][2]) {
+                                          int wn0, int lane, double (&acc)[DM_MB][DM_NB][2],
+                                          const double* amean = nullptr, const double* bmean = nullptr,
+                                          int kvalid = DM_BK) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int k0 = 0; k0 < DM_BK; k0 += 4) {
         double a[DM_MB], b[DM_NB];
+        const bool live = !CENTER || (k0 + t < kvalid);
 #pragma unroll
         for (int mb = 0; mb < DM_MB; ++mb) {
             int m = wm0 + mb * 8 + g;
             a[mb] = A_KMAJOR ? As[(k0 + t) * DM_LD_KMAJOR + m] : As[m * DM_LD_MMAJOR + k0 + t];
+            if (CENTER) a[mb] = live ? a[mb] - amean[mb] : 0.0;
         }
 #pragma unroll
         for (int nb = 0; nb < DM_NB; ++nb) {
             int n = wn0 + nb * 8 + g;
             b[nb] = B_KMAJOR ? Bs[(k0 + t) * DM_LD_KMAJOR + n] : Bs[n * DM_LD_MMAJOR + k0 + t];
+            if (CENTER) b[nb] = live ? b[nb] - bmean[nb] : 0.0;
         }
 #pragma unroll
         for (int mb = 0; mb < DM_MB; ++mb)

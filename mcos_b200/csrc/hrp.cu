@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
         for (int kk = 0; kk < kmax; ++kk) {
             double a[4], b[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { a[q] = Si[kk][ty * 4 + q]; b[q] = Sj[kk][tx * 4 + q]; }
+            for (int q = 0; q < 4; ++q) { a[q] = Si[kk][ty + 16 * q]; b[q] = Sj[kk][tx + 16 * q]; }  // lane-contiguous: no bank conflicts
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
     for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            int i = I * EU_T + ty * 4 + p, j = J * EU_T + tx * 4 + q;
+            int i = I * EU_T + ty + 16 * p, j = J * EU_T + tx + 16 * q;
             if (i < N && j < N) {
                 double v = sqrt(acc[p][q]);
                 E[(size_t)i * N + j] = v;

@@ -55,51 +55,62 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
     const bool diag = (I == J);
     const double* x = X + (size_t)s * T * N;
     const double* mu = mean + (size_t)s * N;
-    double* As[2] = {sm, sm + 2 * DM_BK * DM_LD_KMAJOR};
-    double* Bs[2] = {sm + DM_BK * DM_LD_KMAJOR, sm + 3 * DM_BK * DM_LD_KMAJOR};
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
     const int lcol = tid % DM_BM, lk = tid / DM_BM;  // loader mapping: column fixed, k = lk + 2r
     const int acol = I * DM_BM + lcol, bcol = J * DM_BN + lcol;
-    const double amean = (acol < N) ? mu[acol] : 0.0;
-    const double bmean = (bcol < N) ? mu[bcol] : 0.0;
+    const bool aok = acol < N, bok = bcol < N;
+    const double* asrc = x + (aok ? acol : 0);
+    const double* bsrc = x + (bok ? bcol : 0);
 
+    // per-fragment column means (centring happens in registers, the tiles are copied raw)
+    double amean[DM_MB], bmean[DM_NB];
+    {
+        const int g = lane >> 2;
+#pragma unroll
+        for (int mb = 0; mb < DM_MB; ++mb) {
+            int c = I * DM_BM + wm0 + mb * 8 + g;
+            amean[mb] = (c < N) ? mu[c] : 0.0;
+        }
+#pragma unroll
+        for (int nb = 0; nb < DM_NB; ++nb) {
+            int c = J * DM_BN + wn0 + nb * 8 + g;
+            bmean[nb] = (c < N) ? mu[c] : 0.0;
+        }
+    }
     double acc[DM_MB][DM_NB][2];
 #pragma unroll
     for (int a = 0; a < DM_MB; ++a)
 #pragma unroll
         for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    double ra[DM_BK / 2], rb[DM_BK / 2];
-    auto gload = [&](int kbase) {
+    auto issue = [&](int kt, int buf) {
+        double* At = sm + (size_t)buf * 2 * DM_TILE_KMAJOR;
+        double* Bt = At + DM_TILE_KMAJOR;
+        const int kbase = kt * DM_BK;
 #pragma unroll
         for (int r = 0; r < DM_BK / 2; ++r) {
-            int k = kbase + lk + 2 * r;
-            bool ok = k < T;
-            ra[r] = (ok && acol < N) ? x[(size_t)k * N + acol] - amean : 0.0;
-            if (!diag) rb[r] = (ok && bcol < N) ? x[(size_t)k * N + bcol] - bmean : 0.0;
+            const int kk = lk + 2 * r, k = kbase + kk;
+            const bool ok = k < T;
+            cp_async8(&At[kk * DM_LD_KMAJOR + lcol], asrc + (size_t)(ok ? k : 0) * N, ok && aok);
+            if (!diag) cp_async8(&Bt[kk * DM_LD_KMAJOR + lcol], bsrc + (size_t)(ok ? k : 0) * N, ok && bok);
         }
     };
-    auto sstore = [&](int buf) {
-#pragma unroll
-        for (int r = 0; r < DM_BK / 2; ++r) {
-            int k = lk + 2 * r;
-            As[buf][k * DM_LD_KMAJOR + lcol] = ra[r];
-            if (!diag) Bs[buf][k * DM_LD_KMAJOR + lcol] = rb[r];
-        }
-    };
-
     const int nkt = (T + DM_BK - 1) / DM_BK;
-    gload(0);
-    sstore(0);
-    __syncthreads();
+#pragma unroll
+    for (int st = 0; st < DM_STAGES - 1; ++st) {
+        if (st < nkt) issue(st, st);
+        cp_async_commit();
+    }
     for (int kt = 0; kt < nkt; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nkt) gload((kt + 1) * DM_BK);
-        dmma_slab<true, true>(As[buf], diag ? As[buf] : Bs[buf], wm0, wn0, lane, acc);
-        if (kt + 1 < nkt) sstore(buf ^ 1);
+        cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
+        if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
+        cp_async_commit();
+        const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_KMAJOR;
+        const double* Bt = diag ? At : At + DM_TILE_KMAJOR;
+        dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, amean, bmean, T - kt * DM_BK);
     }
 
     // epilogue: scale, write the lower part and its mirror, accumulate Frobenius / trace partials
@@ -216,7 +227,7 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
     const int nt = (N + DM_BM - 1) / DM_BM, ntiles = nt * (nt + 1) / 2;
     double* lwpart = nullptr;
     if (lw) MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWPART, (size_t)S * ntiles * 2, &lwpart));
-    const size_t smem = (size_t)4 * DM_BK * DM_LD_KMAJOR * sizeof(double);
+    const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_KMAJOR * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double scale = lw ? 1.0 / T : 1.0 / (T - 1);
     syrk_kernel<<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);

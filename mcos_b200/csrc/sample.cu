@@ -66,8 +66,6 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
     extern __shared__ double sm[];
     const int J = blockIdx.x;
     const size_t m0 = (size_t)blockIdx.y * DM_BM;
-    double* As[2] = {sm, sm + 2 * DM_BM * DM_LD_MMAJOR};
-    double* Bs[2] = {sm + DM_BM * DM_LD_MMAJOR, sm + 3 * DM_BM * DM_LD_MMAJOR};
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
     const int lk = tid % DM_BK, lr = tid / DM_BK;  // loader: k fixed, row = lr + 16 r
@@ -78,35 +76,35 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
 #pragma unroll
         for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    double ra[8], rb[8];
-    auto gload = [&](int kbase) {
-        int k = kbase + lk;
+    auto issue = [&](int kt, int buf) {
+        double* At = sm + (size_t)buf * 2 * DM_TILE_MMAJOR;
+        double* Bt = At + DM_TILE_MMAJOR;
+        const int k = kt * DM_BK + lk;
+        const bool kok = k < N;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            size_t m = m0 + lr + 16 * r;
-            int j = J * DM_BN + lr + 16 * r;
-            ra[r] = (k < N && m < M) ? Z[m * N + k] : 0.0;
-            rb[r] = (k < N && j < N) ? L[(size_t)j * N + k] : 0.0;
-        }
-    };
-    auto sstore = [&](int buf) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            As[buf][(lr + 16 * r) * DM_LD_MMAJOR + lk] = ra[r];
-            Bs[buf][(lr + 16 * r) * DM_LD_MMAJOR + lk] = rb[r];
+            const int row = lr + 16 * r;
+            const size_t m = m0 + row;
+            const int j = J * DM_BN + row;
+            const bool aok = kok && m < M, bok = kok && j < N;
+            cp_async8(&At[row * DM_LD_MMAJOR + lk], Z + (aok ? m * N + k : 0), aok);
+            cp_async8(&Bt[row * DM_LD_MMAJOR + lk], L + (bok ? (size_t)j * N + k : 0), bok);
         }
     };
     const int kend = min(N, (J + 1) * DM_BN);  // L[j][k] = 0 for k > j
     const int nkt = (kend + DM_BK - 1) / DM_BK;
-    gload(0);
-    sstore(0);
-    __syncthreads();
+#pragma unroll
+    for (int st = 0; st < DM_STAGES - 1; ++st) {
+        if (st < nkt) issue(st, st);
+        cp_async_commit();
+    }
     for (int kt = 0; kt < nkt; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nkt) gload((kt + 1) * DM_BK);
-        dmma_slab<false, false>(As[buf], Bs[buf], wm0, wn0, lane, acc);
-        if (kt + 1 < nkt) sstore(buf ^ 1);
+        cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
+        if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
+        cp_async_commit();
+        const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_MMAJOR;
+        dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc);
     }
     const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
@@ -132,7 +130,7 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     int grid = (int)std::min<size_t>((pairs + 255) / 256, (size_t)ctx->num_sms * 16);
     philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
     MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
-    const size_t smem = (size_t)4 * DM_BM * DM_LD_MMAJOR * sizeof(double);
+    const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t row_tiles = (M + DM_BM - 1) / DM_BM;
     if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");

@@ -5,29 +5,40 @@
 // dsytrd/dlatrd structure instead: inside a panel of NB columns the matrix is NOT updated -- the symmetric
 // matrix-vector product of every step reads the panel-start matrix (lower triangle only, 4 m^2 bytes) and is corrected
 // with the NB accumulated (V, W) pairs held in shared memory -- and the rank-2NB update A -= V W' + W V' is applied once
-// per panel (8 m^2 bytes per NB steps).  Traffic: (4 + 8/NB) N^3 / 3 bytes = 1.5 N^3 at NB = 16: 3.6x less than v1.
+// per panel (8 m^2 bytes per NB steps).  Traffic: (4 + 8/NB) N^3 / 3 bytes.
 //
-// symv on the lower triangle, one CTA (16 warps) per matrix: a warp owns 16-row block-rows (paired long+short for
-// balance) and sweeps 32-column tiles; a lane owns one column of the tile, so  y_c += A[r][c] v[r]  accumulates
-// privately per lane, and  y_r += A[r][c] v[c]  accumulates in 16 registers that are reduced across the warp once per
-// block-row.  Per-warp partial y vectors live in shared memory and are summed in a fixed order (deterministic).
+// symv on the lower triangle, one CTA (NW warps) per matrix, two CTAs per SM so one matrix's reductions and barriers
+// overlap the other's streaming.  The lower triangle is cut into 16-row x 32-column tiles, enumerated block-row by
+// block-row and dealt to the warps in equal contiguous runs.  Inside a tile a lane owns one column:
+//   y_c += A[r][c] v[r]   accumulates privately in the lane;
+//   y_r += A[r][c] v[c]   accumulates in 16 registers, reduced across the warp (halving butterfly, 16 shuffles) when
+//                         the warp leaves the block-row.
+// Per-warp partial y vectors live in shared memory and are summed in a fixed order (deterministic).  The first column
+// of the next step falls out of the sweep (lane 0 of the first tile of every block-row) and is stashed in shared
+// memory, so no step waits on a strided column read from global memory.
 #include "common.cuh"
 
-#define T2_THREADS 512
-#define T2_NW 16
 #define T2_RB 16
 
-template <int NB>
-__global__ void __launch_bounds__(T2_THREADS, 1)
+// tiles before block-row b when block-row i holds (i >> 1) + 1 tiles
+__device__ __forceinline__ int t2_prefix(int b) {
+    const int h = b >> 1;
+    return (b & 1) ? (h + 1) * (h + 1) : h * (h + 1);
+}
+
+template <int NB, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 2 : 1)
 tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, double* __restrict__ eall,
                 double* __restrict__ tauall) {
+    constexpr int NT = NW * 32;
     extern __shared__ double sm[];
     double* Vp = sm;                         // [NB][N]
     double* Wp = Vp + (size_t)NB * N;        // [NB][N]
     double* v = Wp + (size_t)NB * N;         // [N]
     double* y = v + N;                       // [N]
-    double* ypart = y + N;                   // [T2_NW][N]
-    double* tt = ypart + (size_t)T2_NW * N;  // [2 NB]
+    double* colnext = y + N;                 // [N]  column base of the panel-start matrix, stashed by the sweep
+    double* ypart = colnext + N;             // [NW][N]
+    double* tt = ypart + (size_t)NW * N;     // [2 NB]
     double* red = tt + 2 * NB;               // [32]
     __shared__ double s_tau, s_beta;
 
@@ -38,7 +49,7 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
     double* tau = tauall + (size_t)s * N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    for (int i = tid; i < 2 * NB * N; i += T2_THREADS) sm[i] = 0.0;
+    for (int i = tid; i < 2 * NB * N; i += NT) sm[i] = 0.0;
     __syncthreads();
 
     for (int k0 = 0; k0 + 2 < N; k0 += NB) {
@@ -46,16 +57,18 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
         for (int j = 0; j < nbv; ++j) {
             const int k = k0 + j, base = k + 1, m = N - base;
             // ---- 1. column k of the current matrix = panel-start column minus the panel's rank-2j correction ----------
-            for (int i = k + tid; i < N; i += T2_THREADS) {
-                double a = A[(size_t)i * N + k];
-                for (int p = 0; p < j; ++p)
-                    a -= Vp[p * N + i] * Wp[p * N + k] + Wp[p * N + i] * Vp[p * N + k];
+            for (int i = k + tid; i < N; i += NT) {
+                double a = (j == 0) ? A[(size_t)i * N + k] : colnext[i];
+                for (int p = 0; p < j; ++p) {
+                    a = fma(-Vp[p * N + i], Wp[p * N + k], a);
+                    a = fma(-Wp[p * N + i], Vp[p * N + k], a);
+                }
                 y[i] = a;
             }
             __syncthreads();
             // ---- 2. Householder reflector ---------------------------------------------------------------------------
             double xsq = 0.0;
-            for (int i = base + 1 + tid; i < N; i += T2_THREADS) xsq = fma(y[i], y[i], xsq);
+            for (int i = base + 1 + tid; i < N; i += NT) xsq = fma(y[i], y[i], xsq);
             xsq = block_sum(xsq, red);
             if (tid == 0) {
                 const double alpha = y[base];
@@ -74,7 +87,7 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
             const double tk = s_tau;
             {
                 const double scal = (tk != 0.0) ? 1.0 / (y[base] - s_beta) : 0.0;
-                for (int i = base + tid; i < N; i += T2_THREADS) {
+                for (int i = base + tid; i < N; i += NT) {
                     const double vi = (i == base) ? 1.0 : y[i] * scal;
                     v[i] = vi;
                     Vp[j * N + i] = vi;
@@ -88,81 +101,134 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                 for (int i = base + lane; i < N; i += 32) yp[i] = 0.0;
                 __syncwarp();
                 const int nbr = (m + T2_RB - 1) / T2_RB;
-                const int units = (nbr + 1) / 2;
-                for (int u = wid; u < units; u += T2_NW) {
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        const int b = half ? (nbr - 1 - u) : u;
-                        if (half && b == u) break;
+                const int total = t2_prefix(nbr);
+                int t = (int)(((long long)total * wid) / NW);
+                const int t1 = (int)(((long long)total * (wid + 1)) / NW);
+                if (t < t1) {
+                    int h = (int)((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
+                    while ((h + 1) * (h + 2) <= t) ++h;
+                    while (h * (h + 1) > t) --h;
+                    int b = (t >= (h + 1) * (h + 1)) ? 2 * h + 1 : 2 * h;
+                    int jt = t - t2_prefix(b);
+                    while (t < t1) {
                         const int r0 = base + T2_RB * b;
+                        const int ntile = (b >> 1) + 1;
+                        const bool rows_full = (r0 + T2_RB <= N);
                         double vr[T2_RB], rowp[T2_RB];
 #pragma unroll
-                        for (int t = 0; t < T2_RB; ++t) {
-                            vr[t] = (r0 + t < N) ? v[r0 + t] : 0.0;
-                            rowp[t] = 0.0;
+                        for (int q = 0; q < T2_RB; ++q) {
+                            vr[q] = (r0 + q < N) ? v[r0 + q] : 0.0;
+                            rowp[q] = 0.0;
                         }
-                        const int cend = min(r0 + T2_RB - 1, N - 1);
-                        for (int c0 = base; c0 <= cend; c0 += 32) {
+                        for (; jt < ntile && t < t1; ++jt, ++t) {
+                            const int c0 = base + 32 * jt;
                             const int c = c0 + lane;
-                            const bool cact = c <= cend;
-                            const double vc = cact ? v[c] : 0.0;
                             double av[T2_RB];
+                            double vc;
+                            const double* ap = A + (size_t)r0 * N + c;
+                            if (rows_full && c0 + 31 <= r0) {  // interior tile: every column is left of every row
+                                vc = v[c];
 #pragma unroll
-                            for (int t = 0; t < T2_RB; ++t) {
-                                const int r = r0 + t;
-                                av[t] = (cact && r < N && c <= r) ? A[(size_t)r * N + c] : 0.0;
-                            }
-                            double colacc = 0.0;
+                                for (int q = 0; q < T2_RB; ++q) av[q] = ap[(size_t)q * N];
+                                double colacc = 0.0;
 #pragma unroll
-                            for (int t = 0; t < T2_RB; ++t) {
-                                colacc = fma(av[t], vr[t], colacc);
-                                rowp[t] = fma(av[t], (c != r0 + t) ? vc : 0.0, rowp[t]);  // diagonal counted once
+                                for (int q = 0; q < T2_RB; ++q) {
+                                    colacc = fma(av[q], vr[q], colacc);
+                                    rowp[q] = fma(av[q], vc, rowp[q]);
+                                }
+                                yp[c] += colacc;
+                            } else {  // tile touching the diagonal or the bottom edge
+                                const bool cact = c < N;
+                                vc = cact ? v[c] : 0.0;
+#pragma unroll
+                                for (int q = 0; q < T2_RB; ++q) {
+                                    const int r = r0 + q;
+                                    av[q] = (cact && r < N && c <= r) ? ap[(size_t)q * N] : 0.0;
+                                }
+                                double colacc = 0.0;
+#pragma unroll
+                                for (int q = 0; q < T2_RB; ++q) {
+                                    colacc = fma(av[q], vr[q], colacc);
+                                    rowp[q] = fma(av[q], (c != r0 + q) ? vc : 0.0, rowp[q]);  // diagonal counted once
+                                }
+                                if (cact) yp[c] += colacc;
                             }
-                            if (cact) yp[c] += colacc;
+                            if (jt == 0 && lane == 0) {  // column `base`: the next step's column
+#pragma unroll
+                                for (int q = 0; q < T2_RB; ++q)
+                                    if (r0 + q < N) colnext[r0 + q] = av[q];
+                            }
                         }
                         __syncwarp();
-                        double mine = 0.0;
+                        // halving butterfly: 16 row sums over 32 lanes in 16 shuffles; lane L ends with row L >> 1
+                        double r8[8], r4[4], r2[2], r1;
+                        const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
 #pragma unroll
-                        for (int t = 0; t < T2_RB; ++t) {
-                            const double r = warp_sum(rowp[t]);
-                            if (lane == t) mine = r;
+                        for (int q = 0; q < 8; ++q) {
+                            const double send = u16 ? rowp[q] : rowp[q + 8];
+                            const double keep = u16 ? rowp[q + 8] : rowp[q];
+                            r8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                         }
-                        if (lane < T2_RB && r0 + lane < N) yp[r0 + lane] += mine;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double send = u8 ? r8[q] : r8[q + 4];
+                            const double keep = u8 ? r8[q + 4] : r8[q];
+                            r4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const double send = u4 ? r4[q] : r4[q + 2];
+                            const double keep = u4 ? r4[q + 2] : r4[q];
+                            r2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        {
+                            const double send = u2 ? r2[0] : r2[1];
+                            const double keep = u2 ? r2[1] : r2[0];
+                            r1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+                        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+                        const int rr = r0 + (lane >> 1);
+                        if (!(lane & 1) && rr < N) yp[rr] += r1;
                         __syncwarp();
+                        ++b;
+                        jt = 0;
                     }
                 }
             }
             __syncthreads();
-            for (int i = base + tid; i < N; i += T2_THREADS) {
-                double t = 0.0;
+            for (int i = base + tid; i < N; i += NT) {
+                double acc = 0.0;
 #pragma unroll
-                for (int w = 0; w < T2_NW; ++w) t += ypart[(size_t)w * N + i];
-                y[i] = t;
+                for (int w = 0; w < NW; ++w) acc += ypart[(size_t)w * N + i];
+                y[i] = acc;
             }
             // ---- 4. panel corrections: y -= V (W'v) + W (V'v) -------------------------------------------------------
-            if (wid < j) {
-                double t1 = 0.0, t2 = 0.0;
+            for (int p = wid; p < j; p += NW) {
+                double t1s = 0.0, t2s = 0.0;
                 for (int i = base + lane; i < N; i += 32) {
                     const double vi = v[i];
-                    t1 = fma(Wp[wid * N + i], vi, t1);
-                    t2 = fma(Vp[wid * N + i], vi, t2);
+                    t1s = fma(Wp[p * N + i], vi, t1s);
+                    t2s = fma(Vp[p * N + i], vi, t2s);
                 }
-                t1 = warp_sum(t1);
-                t2 = warp_sum(t2);
-                if (lane == 0) { tt[wid] = t1; tt[NB + wid] = t2; }
+                t1s = warp_sum(t1s);
+                t2s = warp_sum(t2s);
+                if (lane == 0) { tt[p] = t1s; tt[NB + p] = t2s; }
             }
             __syncthreads();
             double dot = 0.0;
-            for (int i = base + tid; i < N; i += T2_THREADS) {
+            for (int i = base + tid; i < N; i += NT) {
                 double yi = y[i];
-                for (int p = 0; p < j; ++p) yi -= Vp[p * N + i] * tt[p] + Wp[p * N + i] * tt[NB + p];
+                for (int p = 0; p < j; ++p) {
+                    yi = fma(-Vp[p * N + i], tt[p], yi);
+                    yi = fma(-Wp[p * N + i], tt[NB + p], yi);
+                }
                 y[i] = yi;
                 dot = fma(tk * yi, v[i], dot);
             }
             // ---- 5. w = tau y - (tau/2)(tau y . v) v ----------------------------------------------------------------
             dot = block_sum(dot, red);
             const double a2 = -0.5 * tk * dot;
-            for (int i = base + tid; i < N; i += T2_THREADS) Wp[j * N + i] = tk * y[i] + a2 * v[i];
+            for (int i = base + tid; i < N; i += NT) Wp[j * N + i] = fma(tk, y[i], a2 * v[i]);
             __syncthreads();
         }
         // ---- panel flush: A[i][c] -= sum_p V[p][i] W[p][c] + W[p][i] V[p][c]  for i >= c >= k1 -----------------------
@@ -170,10 +236,10 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
         const int mm = N - k1;
         const int nch = (mm + 31) >> 5;
         const int units = (nch + 1) / 2;
-        const int nrg = (units >= T2_NW) ? 1 : T2_NW / units;
-        if (units >= T2_NW || wid < units * nrg) {
-            const int rg = (units >= T2_NW) ? 0 : wid / units;
-            for (int u = (units >= T2_NW) ? wid : wid % units; u < units; u += T2_NW) {
+        const int nrg = (units >= NW) ? 1 : NW / units;
+        if (units >= NW || wid < units * nrg) {
+            const int rg = (units >= NW) ? 0 : wid / units;
+            for (int u = (units >= NW) ? wid : wid % units; u < units; u += NW) {
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     const int ch = half ? (nch - 1 - u) : u;
@@ -183,15 +249,19 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                     double vc[NB], wc[NB];
 #pragma unroll
                     for (int p = 0; p < NB; ++p) {
-                        vc[p] = (act && p < nbv) ? Vp[p * N + c] : 0.0;
-                        wc[p] = (act && p < nbv) ? Wp[p * N + c] : 0.0;
+                        vc[p] = (act && p < nbv) ? -Vp[p * N + c] : 0.0;
+                        wc[p] = (act && p < nbv) ? -Wp[p * N + c] : 0.0;
                     }
+                    double* colp = A + c;
                     for (int i = k1 + 32 * ch + rg; i < N; i += nrg) {
                         if (act && c <= i) {
-                            double a = A[(size_t)i * N + c];
+                            double a = colp[(size_t)i * N];
 #pragma unroll
-                            for (int p = 0; p < NB; ++p) a -= Vp[p * N + i] * wc[p] + Wp[p * N + i] * vc[p];
-                            A[(size_t)i * N + c] = a;
+                            for (int p = 0; p < NB; ++p) {
+                                a = fma(Vp[p * N + i], wc[p], a);
+                                a = fma(Wp[p * N + i], vc[p], a);
+                            }
+                            colp[(size_t)i * N] = a;
                         }
                     }
                 }
@@ -214,23 +284,22 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
     }
 }
 
-static size_t t2_smem(int N, int nb) { return ((size_t)(2 * nb + 2 + T2_NW) * N + 2 * nb + 32) * sizeof(double); }
+template <int NB, int NW>
+static size_t t2_smem(int N) { return ((size_t)(2 * NB + 3 + NW) * N + 2 * NB + 32) * sizeof(double); }
+
+template <int NB, int NW>
+static int t2_launch(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau) {
+    const size_t smem = t2_smem<NB, NW>(ctx->N);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag2_kernel<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tridiag2_kernel<NB, NW><<<S, NW * 32, smem, ctx->stream>>>(A, ctx->N, d, e, tau);
+    return 1;
+}
 
 // Returns 1 if launched, 0 if this size is not supported (caller falls back to tridiag_kernel), <0 on error.
 int mcosb_launch_tridiag2(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau) {
     const int N = ctx->N;
     if (N < 96) return 0;  // small matrices: the fused v1 kernel is already cheap and has less fixed overhead
-    if (t2_smem(N, 16) <= (size_t)ctx->smem_optin) {
-        const size_t smem = t2_smem(N, 16);
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tridiag2_kernel<16><<<S, T2_THREADS, smem, ctx->stream>>>(A, N, d, e, tau);
-        return 1;
-    }
-    if (t2_smem(N, 8) <= (size_t)ctx->smem_optin) {
-        const size_t smem = t2_smem(N, 8);
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tridiag2_kernel<8><<<S, T2_THREADS, smem, ctx->stream>>>(A, N, d, e, tau);
-        return 1;
-    }
+    // 8 warps + panels of 8 keep the footprint at 27 N doubles: two matrices per SM up to N ~ 520, one beyond
+    if (t2_smem<8, 8>(N) <= (size_t)ctx->smem_optin) return t2_launch<8, 8>(ctx, S, A, d, e, tau);
     return 0;
 }
