@@ -7,18 +7,25 @@
 // with the NB accumulated (V, W) pairs held in shared memory -- and the rank-2NB update A -= V W' + W V' is applied once
 // per panel (8 m^2 bytes per NB steps).  Traffic: (4 + 8/NB) N^3 / 3 bytes.
 //
-// symv on the lower triangle, one CTA (NW warps) per matrix, two CTAs per SM so one matrix's reductions and barriers
-// overlap the other's streaming.  The lower triangle is cut into 16-row x 32-column tiles, enumerated block-row by
+// symv on the lower triangle, one CTA (NW warps) per matrix.  The lower triangle is cut into 16-row x 32-column tiles, enumerated block-row by
 // block-row and dealt to the warps in equal contiguous runs.  Inside a tile a lane owns one column:
 //   y_c += A[r][c] v[r]   accumulates privately in the lane;
 //   y_r += A[r][c] v[c]   accumulates in 16 registers, reduced across the warp (halving butterfly, 16 shuffles) when
 //                         the warp leaves the block-row.
+// The 16 loads of the next tile are issued before the current tile is consumed (register double buffering), and the
+// FP64 accumulations are split into independent chains: measured with clock64 (T2_TIMING), dependent DFMA issue
+// latency and one-tile-in-flight memory latency, not bandwidth, bound this kernel.
 // Per-warp partial y vectors live in shared memory and are summed in a fixed order (deterministic).  The first column
 // of the next step falls out of the sweep (lane 0 of the first tile of every block-row) and is stashed in shared
 // memory, so no step waits on a strided column read from global memory.
 #include "common.cuh"
 
 #define T2_RB 16
+#ifdef T2_TIMING
+#define T2_TICK(idx) do { if (threadIdx.x == 0) { long long now__ = clock64(); t2_acc[idx] += now__ - t2_last; t2_last = now__; } } while (0)
+#else
+#define T2_TICK(idx) do { } while (0)
+#endif
 
 // tiles before block-row b when block-row i holds (i >> 1) + 1 tiles
 __device__ __forceinline__ int t2_prefix(int b) {
@@ -27,7 +34,7 @@ __device__ __forceinline__ int t2_prefix(int b) {
 }
 
 template <int NB, int NW>
-__global__ void __launch_bounds__(NW * 32, (NW <= 8) ? 2 : 1)
+__global__ void __launch_bounds__(NW * 32, 1)
 tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, double* __restrict__ eall,
                 double* __restrict__ tauall) {
     constexpr int NT = NW * 32;
@@ -51,6 +58,11 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
 
     for (int i = tid; i < 2 * NB * N; i += NT) sm[i] = 0.0;
     __syncthreads();
+#ifdef T2_TIMING
+    long long t2_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t2_last = clock64();
+    long long t2_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
     for (int k0 = 0; k0 + 2 < N; k0 += NB) {
         const int nbv = min(NB, N - 2 - k0);
@@ -66,6 +78,7 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                 y[i] = a;
             }
             __syncthreads();
+            T2_TICK(0);
             // ---- 2. Householder reflector ---------------------------------------------------------------------------
             double xsq = 0.0;
             for (int i = base + 1 + tid; i < N; i += NT) xsq = fma(y[i], y[i], xsq);
@@ -95,6 +108,7 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                 }
             }
             __syncthreads();
+            T2_TICK(1);
             // ---- 3. y = A_sym(base.., base..) v from the lower triangle of the panel-start matrix --------------------
             {
                 double* yp = ypart + (size_t)wid * N;
@@ -110,10 +124,26 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                     while (h * (h + 1) > t) --h;
                     int b = (t >= (h + 1) * (h + 1)) ? 2 * h + 1 : 2 * h;
                     int jt = t - t2_prefix(b);
+                    // register double buffering: the 16 loads of tile t+1 are in flight while tile t is consumed
+                    auto load_tile = [&](int bb, int jj, double (&dst)[T2_RB]) {
+                        const int r0i = base + T2_RB * bb, c0i = base + 32 * jj, ci = c0i + lane;
+                        if (r0i + T2_RB <= N && c0i + 31 <= r0i) {
+                            const double* src = A + (size_t)r0i * N + ci;
+#pragma unroll
+                            for (int q = 0; q < T2_RB; ++q) dst[q] = __ldcg(src + (size_t)q * N);   // independent addresses
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < T2_RB; ++q) {
+                                const int r = r0i + q;
+                                dst[q] = ((ci < N) && (r < N) && (ci <= r)) ? __ldcg(A + (size_t)r * N + ci) : 0.0;
+                            }
+                        }
+                    };
+                    double nxt[T2_RB];
+                    load_tile(b, jt, nxt);
                     while (t < t1) {
                         const int r0 = base + T2_RB * b;
                         const int ntile = (b >> 1) + 1;
-                        const bool rows_full = (r0 + T2_RB <= N);
                         double vr[T2_RB], rowp[T2_RB];
 #pragma unroll
                         for (int q = 0; q < T2_RB; ++q) {
@@ -121,44 +151,59 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                             rowp[q] = 0.0;
                         }
                         for (; jt < ntile && t < t1; ++jt, ++t) {
-                            const int c0 = base + 32 * jt;
-                            const int c = c0 + lane;
                             double av[T2_RB];
-                            double vc;
-                            const double* ap = A + (size_t)r0 * N + c;
-                            if (rows_full && c0 + 31 <= r0) {  // interior tile: every column is left of every row
-                                vc = v[c];
+#ifdef T2_TIMING
+                            long long c_a = clock64();
+#endif
 #pragma unroll
-                                for (int q = 0; q < T2_RB; ++q) av[q] = ap[(size_t)q * N];
-                                double colacc = 0.0;
+                            for (int q = 0; q < T2_RB; ++q) av[q] = nxt[q];
+#ifdef T2_TIMING
+                            if (av[0] == 1.2345e-300) t2_dbg[7] += 1;   // force the loads to be complete here
+                            long long c_b = clock64();
+                            if (wid == 0) t2_dbg[0] += c_b - c_a;
+#endif
+                            if (t + 1 < t1) {
+                                int b2 = b, j2 = jt + 1;
+                                if (j2 >= ntile) { j2 = 0; ++b2; }
+                                load_tile(b2, j2, nxt);
+                            }
+#ifdef T2_TIMING
+                            long long c_c = clock64();
+                            if (wid == 0) t2_dbg[1] += c_c - c_b;
+#endif
+                            const int c0 = base + 32 * jt, c = c0 + lane;
+                            if (c0 + 31 <= r0) {  // no diagonal element in this tile
+                                const double vc = v[c];
+                                double ca[4] = {0.0, 0.0, 0.0, 0.0};   // four chains: FP64 dependent-issue latency is long
 #pragma unroll
                                 for (int q = 0; q < T2_RB; ++q) {
-                                    colacc = fma(av[q], vr[q], colacc);
+                                    ca[q & 3] = fma(av[q], vr[q], ca[q & 3]);
                                     rowp[q] = fma(av[q], vc, rowp[q]);
                                 }
-                                yp[c] += colacc;
-                            } else {  // tile touching the diagonal or the bottom edge
+                                yp[c] += (ca[0] + ca[1]) + (ca[2] + ca[3]);
+                            } else {
                                 const bool cact = c < N;
-                                vc = cact ? v[c] : 0.0;
+                                const double vc = cact ? v[c] : 0.0;
+                                double ca[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                                 for (int q = 0; q < T2_RB; ++q) {
-                                    const int r = r0 + q;
-                                    av[q] = (cact && r < N && c <= r) ? ap[(size_t)q * N] : 0.0;
-                                }
-                                double colacc = 0.0;
-#pragma unroll
-                                for (int q = 0; q < T2_RB; ++q) {
-                                    colacc = fma(av[q], vr[q], colacc);
+                                    ca[q & 3] = fma(av[q], vr[q], ca[q & 3]);
                                     rowp[q] = fma(av[q], (c != r0 + q) ? vc : 0.0, rowp[q]);  // diagonal counted once
                                 }
-                                if (cact) yp[c] += colacc;
+                                if (cact) yp[c] += (ca[0] + ca[1]) + (ca[2] + ca[3]);
                             }
                             if (jt == 0 && lane == 0) {  // column `base`: the next step's column
 #pragma unroll
                                 for (int q = 0; q < T2_RB; ++q)
                                     if (r0 + q < N) colnext[r0 + q] = av[q];
                             }
+#ifdef T2_TIMING
+                            if (wid == 0) { t2_dbg[2] += clock64() - c_c; t2_dbg[3] += 1; }
+#endif
                         }
+#ifdef T2_TIMING
+                        long long c_r = clock64();
+#endif
                         __syncwarp();
                         // halving butterfly: 16 row sums over 32 lanes in 16 shuffles; lane L ends with row L >> 1
                         double r8[8], r4[4], r2[2], r1;
@@ -190,12 +235,16 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                         const int rr = r0 + (lane >> 1);
                         if (!(lane & 1) && rr < N) yp[rr] += r1;
                         __syncwarp();
+#ifdef T2_TIMING
+                        if (wid == 0) { t2_dbg[4] += clock64() - c_r; t2_dbg[5] += 1; }
+#endif
                         ++b;
                         jt = 0;
                     }
                 }
             }
             __syncthreads();
+            T2_TICK(2);
             for (int i = base + tid; i < N; i += NT) {
                 double acc = 0.0;
 #pragma unroll
@@ -215,6 +264,7 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                 if (lane == 0) { tt[p] = t1s; tt[NB + p] = t2s; }
             }
             __syncthreads();
+            T2_TICK(3);
             double dot = 0.0;
             for (int i = base + tid; i < N; i += NT) {
                 double yi = y[i];
@@ -230,6 +280,7 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
             const double a2 = -0.5 * tk * dot;
             for (int i = base + tid; i < N; i += NT) Wp[j * N + i] = fma(tk, y[i], a2 * v[i]);
             __syncthreads();
+            T2_TICK(4);
         }
         // ---- panel flush: A[i][c] -= sum_p V[p][i] W[p][c] + W[p][i] V[p][c]  for i >= c >= k1 -----------------------
         const int k1 = k0 + nbv;
@@ -253,7 +304,24 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                         wc[p] = (act && p < nbv) ? -Wp[p * N + c] : 0.0;
                     }
                     double* colp = A + c;
-                    for (int i = k1 + 32 * ch + rg; i < N; i += nrg) {
+                    int i = k1 + 32 * ch + rg;
+                    for (; i + 3 * nrg < N; i += 4 * nrg) {   // four rows in flight per lane
+                        double a4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) a4[q] = (act && c <= i + q * nrg) ? colp[(size_t)(i + q * nrg) * N] : 0.0;
+#pragma unroll
+                        for (int p = 0; p < NB; ++p) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                a4[q] = fma(Vp[p * N + i + q * nrg], wc[p], a4[q]);
+                                a4[q] = fma(Wp[p * N + i + q * nrg], vc[p], a4[q]);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (act && c <= i + q * nrg) colp[(size_t)(i + q * nrg) * N] = a4[q];
+                    }
+                    for (; i < N; i += nrg) {
                         if (act && c <= i) {
                             double a = colp[(size_t)i * N];
 #pragma unroll
@@ -268,7 +336,14 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
             }
         }
         __syncthreads();
+        T2_TICK(5);
     }
+#ifdef T2_TIMING
+    if (tid == 0 && blockIdx.x == 0)
+        printf("warp0: wait %lld issue %lld compute %lld tiles %lld reduce %lld blockrows %lld\n", t2_dbg[0], t2_dbg[1], t2_dbg[2], t2_dbg[3], t2_dbg[4], t2_dbg[5]);
+    if (tid == 0 && blockIdx.x == 0)
+        printf("t2 cycles: col %lld refl %lld sweep %lld ysum+t12 %lld corr+w %lld flush %lld\n", t2_acc[0], t2_acc[1], t2_acc[2], t2_acc[3], t2_acc[4], t2_acc[5]);
+#endif
     if (tid == 0) {
         if (N == 1) {
             d[0] = A[0];
@@ -285,7 +360,9 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
 }
 
 template <int NB, int NW>
-static size_t t2_smem(int N) { return ((size_t)(2 * NB + 3 + NW) * N + 2 * NB + 32) * sizeof(double); }
+static size_t t2_smem(int N) {
+    return ((size_t)(2 * NB + 3 + NW) * N + 2 * NB + 32 ) * sizeof(double);
+}
 
 template <int NB, int NW>
 static int t2_launch(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau) {
