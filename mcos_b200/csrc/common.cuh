@@ -46,6 +46,8 @@ enum KernelId {
     MK_NCO_CLUSTER,
     MK_NCO_ALLOC,
     MK_TRIDIAG2,
+    MK_HRP_PERMUTE,
+    MK_HRP_BISECT,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -70,7 +72,9 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "nco_dist",
     "nco_cluster",
     "nco_alloc",
-    "tridiag2"
+    "tridiag2",
+    "hrp_permute",
+    "hrp_bisect"
 };
 
 struct mcosb_ctx {

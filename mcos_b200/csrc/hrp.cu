@@ -125,10 +125,7 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
     const double* C = cov_all + (size_t)s * N * N;
 
     if (N == 1) {
-        if (tid == 0) {
-            w_all[s] = 1.0;
-            if (order_all) order_all[s] = 0;
-        }
+        if (tid == 0) order_all[s] = 0;
         return;
     }
     // ---- Prim's MST from node 0 (scipy _hierarchy.mst_single_linkage) -------------------------------------------------
@@ -217,19 +214,58 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
             Z[r * 4 + 0] = sa[r]; Z[r * 4 + 1] = sb[r]; Z[r * 4 + 2] = sdist[r]; Z[r * 4 + 3] = csize[N + r];
         }
     }
-    if (order_all)
-        for (int i = tid; i < N; i += TR_THREADS) order_all[(size_t)s * N + i] = order[i];
-    // ---- recursive bisection, level by level --------------------------------------------------------------------------
-    double* wpos = best;
-    double* cvar = edist;   // [<= N] cluster variance per child segment
-    for (int i = tid; i < N; i += TR_THREADS) wpos[i] = 1.0;
+    for (int i = tid; i < N; i += TR_THREADS) order_all[(size_t)s * N + i] = order[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// P[a][b] = C[order[a]][order[b]]: the covariance in quasi-diagonal order, so every cluster of the bisection is a
+// contiguous square block that can be read coalesced.  grid = (ceil(N/8), S), one warp per row; the gather stays inside
+// one 8N-byte row of C (L1-resident after the first touch).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hrp_permute_kernel(const double* __restrict__ cov_all,
+                                                          const int* __restrict__ order_all, int N,
+                                                          double* __restrict__ P_all) {
+    const int s = blockIdx.y;
+    const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (a >= N) return;
+    const int* order = order_all + (size_t)s * N;
+    const double* row = cov_all + (size_t)s * N * N + (size_t)order[a] * N;
+    double* dst = P_all + (size_t)s * N * N + (size_t)a * N;
+    for (int b = lane; b < N; b += 32) dst[b] = row[order[b]];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Recursive bisection (optimizer.py:256-279), level by level, on the permuted covariance.  One CTA per simulation.
+// Cluster variance of [lo, hi): w = ivp / sum(ivp), ivp_a = 1 / P[a][a];  var = w' P[lo:hi, lo:hi] w.
+// ---------------------------------------------------------------------------------------------------------------
+#define BS_THREADS 256
+#define BS_BIG 64   // clusters longer than this are reduced by the whole CTA, shorter ones by one warp each
+
+__global__ void __launch_bounds__(BS_THREADS) hrp_bisect_kernel(const double* __restrict__ P_all, int N,
+                                                                double* __restrict__ w_all, int* __restrict__ status) {
+    extern __shared__ double sm[];
+    double* u = sm;            // [N] inverse variances in position order
+    double* wpos = u + N;      // [N]
+    double* cvar = wpos + N;   // [N]
+    double* red = cvar + N;    // [32]
+    int* segA = reinterpret_cast<int*>(red + 32);  // [N+1]
+    int* segB = segA + N + 1;                      // [N+1]
+    __shared__ int s_nseg;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int NW = BS_THREADS / 32;
+    const double* P = P_all + (size_t)s * N * N;
+    for (int i = tid; i < N; i += BS_THREADS) {
+        u[i] = 1.0 / P[(size_t)i * N + i];
+        wpos[i] = 1.0;
+    }
+    if (tid == 0) { segA[0] = 0; segA[1] = N; s_nseg = 1; }
     int* cur = segA;
     int* nxt = segB;
     while (true) {
         __syncthreads();
         const int nseg = s_nseg;
         __syncthreads();  // everyone has read s_nseg before thread 0 overwrites it below
-        // children boundaries: segment q = [cur[q], cur[q+1]) splits at lo + ceil(len/2) when len >= 2
         bool any_split = false;
         for (int q = 0; q < nseg; ++q) any_split |= (cur[q + 1] - cur[q] >= 2);   // uniform
         if (!any_split) break;
@@ -238,37 +274,51 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
             for (int q = 0; q < nseg; ++q) {
                 int lo = cur[q], hi = cur[q + 1], len = hi - lo;
                 nxt[nn++] = lo;
-                if (len >= 2) nxt[nn++] = lo + (len + 1) / 2;
+                if (len >= 2) nxt[nn++] = lo + (len + 1) / 2;   // np.array_split: the first half gets the extra item
             }
             nxt[nn] = N;
             s_nseg = nn;
         }
         __syncthreads();
         const int nchild = s_nseg;
-        // cluster variance of every child that came from a split (warp per child; lanes stride the a-b pairs)
+        // big clusters: the whole CTA, one after the other (only the first few levels have any)
+        for (int ch = 0; ch < nchild; ++ch) {
+            const int lo = nxt[ch], hi = nxt[ch + 1], len = hi - lo;
+            if (len <= BS_BIG) continue;
+            double isum = 0.0;
+            for (int a = tid; a < len; a += BS_THREADS) isum += u[lo + a];
+            isum = block_sum(isum, red);
+            double q = 0.0;
+            for (int a = wid; a < len; a += NW) {
+                const double ua = u[lo + a];
+                const double* row = P + (size_t)(lo + a) * N + lo;
+                double part = 0.0;
+                for (int b = lane; b < len; b += 32) part = fma(u[lo + b], row[b], part);
+                q = fma(ua, part, q);
+            }
+            q = block_sum(q, red);
+            if (tid == 0) cvar[ch] = q / (isum * isum);
+        }
+        // small clusters: one warp each
         for (int ch = wid; ch < nchild; ch += NW) {
             const int lo = nxt[ch], hi = nxt[ch + 1], len = hi - lo;
+            if (len > BS_BIG) continue;
             double isum = 0.0;
-            for (int a = lane; a < len; a += 32) { int oa = order[lo + a]; isum += 1.0 / C[(size_t)oa * N + oa]; }
+            for (int a = lane; a < len; a += 32) isum += u[lo + a];
             isum = warp_sum(isum);
             double q = 0.0;
             for (int idx = lane; idx < len * len; idx += 32) {
-                int a = idx / len, b = idx - a * len;
-                int oa = order[lo + a], ob = order[lo + b];
-                double wa = (1.0 / C[(size_t)oa * N + oa]) / isum, wb = (1.0 / C[(size_t)ob * N + ob]) / isum;
-                q = fma(wa * wb, C[(size_t)oa * N + ob], q);
+                const int a = idx / len, b = idx - a * len;
+                q = fma(u[lo + a] * u[lo + b], P[(size_t)(lo + a) * N + lo + b], q);
             }
             q = warp_sum(q);
-            if (lane == 0) cvar[ch] = q;
+            if (lane == 0) cvar[ch] = q / (isum * isum);
         }
         __syncthreads();
-        // apply the allocation factors: walk parents and their children in step
-        for (int i = tid; i < N; i += TR_THREADS) {
-            // find the child segment containing position i (binary search over nxt)
+        for (int i = tid; i < N; i += BS_THREADS) {
             int lo = 0, hi = nchild;
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (nxt[mid] <= i) lo = mid; else hi = mid; }
             const int ch = lo;
-            // parent segment: binary search over cur
             int pl = 0, ph = nseg;
             while (ph - pl > 1) { int mid = (pl + ph) >> 1; if (cur[mid] <= i) pl = mid; else ph = mid; }
             const int plo = cur[pl], phi = cur[pl + 1];
@@ -284,7 +334,7 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
         int* t = cur; cur = nxt; nxt = t;
     }
     double part = 0.0;
-    for (int i = tid; i < N; i += TR_THREADS) {
+    for (int i = tid; i < N; i += BS_THREADS) {
         double wv = wpos[i];
         w_all[(size_t)s * N + i] = wv;
         part += wv;
@@ -311,11 +361,20 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
     const int nt = (N + EU_T - 1) / EU_T;
     hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, N, E);
     MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
+    int* order = dorder;
+    if (!order) MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_ORDER, (size_t)S * n, &order));
     size_t smem = (3 * n + 32) * sizeof(double) + (4 * n + 4 * n + n + 2 * (n + 1) + n + 32) * sizeof(int);
     if (smem > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for hrp_tree_kernel");
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hrp_tree_kernel<<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, dorder, dlink, dstatus);
+    hrp_tree_kernel<<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus);
     MCOSB_LAUNCHED(ctx, MK_HRP_TREE);
+    double* P = D;  // the distance matrix is dead once E exists: reuse its buffer for the permuted covariance
+    hrp_permute_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, order, N, P);
+    MCOSB_LAUNCHED(ctx, MK_HRP_PERMUTE);
+    size_t smem_b = (3 * n + 32) * sizeof(double) + (2 * (n + 1)) * sizeof(int);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    hrp_bisect_kernel<<<S, BS_THREADS, smem_b, ctx->stream>>>(P, N, dw, dstatus);
+    MCOSB_LAUNCHED(ctx, MK_HRP_BISECT);
     return MCOSB_OK;
 }
 
