@@ -20,20 +20,59 @@
 // memory, so no step waits on a strided column read from global memory.
 #include "common.cuh"
 
-#define T2_RB 16
 #ifdef T2_TIMING
 #define T2_TICK(idx) do { if (threadIdx.x == 0) { long long now__ = clock64(); t2_acc[idx] += now__ - t2_last; t2_last = now__; } } while (0)
 #else
 #define T2_TICK(idx) do { } while (0)
 #endif
 
-// tiles before block-row b when block-row i holds (i >> 1) + 1 tiles
+// Block-row i (RB rows) holds RB (i + 1) columns = i / G + 1 tiles of 32 columns, G = 32 / RB.
+// Tiles before block-row b = G h + r:  G h (h + 1) / 2 + r (h + 1).
+template <int RB>
+__device__ __forceinline__ int t2_ntile(int b) { return b / (32 / RB) + 1; }
+template <int RB>
 __device__ __forceinline__ int t2_prefix(int b) {
-    const int h = b >> 1;
-    return (b & 1) ? (h + 1) * (h + 1) : h * (h + 1);
+    constexpr int G = 32 / RB;
+    const int h = b / G, r = b % G;
+    return G * h * (h + 1) / 2 + r * (h + 1);
+}
+template <int RB>
+__device__ __forceinline__ int t2_block_of_tile(int t) {
+    constexpr int G = 32 / RB;
+    int h = (int)((sqrt(1.0 + 8.0 * t / G) - 1.0) * 0.5);
+    while (G * (h + 1) * (h + 2) / 2 <= t) ++h;
+    while (G * h * (h + 1) / 2 > t) --h;
+    return G * h + (t - G * h * (h + 1) / 2) / (h + 1);
 }
 
-template <int NB, int NW>
+// Sum RB per-lane row partials over the 32 lanes with a halving butterfly; the lane with (lane % (32 / RB)) == 0 and
+// index lane / (32 / RB) ends up owning the total of row lane / (32 / RB).
+template <int RB>
+__device__ __forceinline__ double t2_row_reduce(double (&rowp)[RB], int lane) {
+    double cur[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) cur[q] = rowp[q];
+    int width = RB;
+#pragma unroll
+    for (int bit = 16; bit >= 32 / RB; bit >>= 1) {   // RB -> RB/2 -> ... -> 1 values per lane
+        const bool up = lane & bit;
+        width >>= 1;
+#pragma unroll
+        for (int q = 0; q < RB / 2; ++q) {
+            if (q < width) {
+                const double send = up ? cur[q] : cur[q + width];
+                const double keep = up ? cur[q + width] : cur[q];
+                cur[q] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+        }
+    }
+    double r = cur[0];
+#pragma unroll
+    for (int bit = 32 / RB / 2; bit >= 1; bit >>= 1) r += __shfl_xor_sync(0xffffffffu, r, bit);
+    return r;
+}
+
+template <int NB, int NW, int RB>
 __global__ void __launch_bounds__(NW * 32, 1)
 tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, double* __restrict__ eall,
                 double* __restrict__ tauall) {
@@ -114,69 +153,58 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                 double* yp = ypart + (size_t)wid * N;
                 for (int i = base + lane; i < N; i += 32) yp[i] = 0.0;
                 __syncwarp();
-                const int nbr = (m + T2_RB - 1) / T2_RB;
-                const int total = t2_prefix(nbr);
+                const int nbr = (m + RB - 1) / RB;
+                const int total = t2_prefix<RB>(nbr);
                 int t = (int)(((long long)total * wid) / NW);
                 const int t1 = (int)(((long long)total * (wid + 1)) / NW);
                 if (t < t1) {
-                    int h = (int)((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
-                    while ((h + 1) * (h + 2) <= t) ++h;
-                    while (h * (h + 1) > t) --h;
-                    int b = (t >= (h + 1) * (h + 1)) ? 2 * h + 1 : 2 * h;
-                    int jt = t - t2_prefix(b);
-                    // register double buffering: the 16 loads of tile t+1 are in flight while tile t is consumed
-                    auto load_tile = [&](int bb, int jj, double (&dst)[T2_RB]) {
-                        const int r0i = base + T2_RB * bb, c0i = base + 32 * jj, ci = c0i + lane;
-                        if (r0i + T2_RB <= N && c0i + 31 <= r0i) {
+                    int b = t2_block_of_tile<RB>(t);
+                    int jt = t - t2_prefix<RB>(b);
+                    // register pipeline: the loads of the next two tiles are in flight while one tile is consumed
+                    auto load_tile = [&](int bb, int jj, double (&dst)[RB]) {
+                        const int r0i = base + RB * bb, c0i = base + 32 * jj, ci = c0i + lane;
+                        if (r0i + RB <= N && c0i + 31 <= r0i) {
                             const double* src = A + (size_t)r0i * N + ci;
 #pragma unroll
-                            for (int q = 0; q < T2_RB; ++q) dst[q] = __ldcg(src + (size_t)q * N);   // independent addresses
+                            for (int q = 0; q < RB; ++q) dst[q] = __ldcg(src + (size_t)q * N);   // independent addresses
                         } else {
 #pragma unroll
-                            for (int q = 0; q < T2_RB; ++q) {
+                            for (int q = 0; q < RB; ++q) {
                                 const int r = r0i + q;
                                 dst[q] = ((ci < N) && (r < N) && (ci <= r)) ? __ldcg(A + (size_t)r * N + ci) : 0.0;
                             }
                         }
                     };
-                    double nxt[T2_RB];
-                    load_tile(b, jt, nxt);
+                    auto advance = [&](int& bb, int& jj) {
+                        if (++jj >= t2_ntile<RB>(bb)) { jj = 0; ++bb; }
+                    };
+                    double n1[RB], n2[RB];
+                    int b1 = b, j1 = jt;          // tile t (held in n1), then t + 1 (n2)
+                    load_tile(b1, j1, n1);
+                    int b2 = b1, j2 = j1;
+                    advance(b2, j2);
+                    if (t + 1 < t1) load_tile(b2, j2, n2);
                     while (t < t1) {
-                        const int r0 = base + T2_RB * b;
-                        const int ntile = (b >> 1) + 1;
-                        double vr[T2_RB], rowp[T2_RB];
+                        const int r0 = base + RB * b;
+                        const int ntile = t2_ntile<RB>(b);
+                        double vr[RB], rowp[RB];
 #pragma unroll
-                        for (int q = 0; q < T2_RB; ++q) {
+                        for (int q = 0; q < RB; ++q) {
                             vr[q] = (r0 + q < N) ? v[r0 + q] : 0.0;
                             rowp[q] = 0.0;
                         }
                         for (; jt < ntile && t < t1; ++jt, ++t) {
-                            double av[T2_RB];
-#ifdef T2_TIMING
-                            long long c_a = clock64();
-#endif
+                            double av[RB];
 #pragma unroll
-                            for (int q = 0; q < T2_RB; ++q) av[q] = nxt[q];
-#ifdef T2_TIMING
-                            if (av[0] == 1.2345e-300) t2_dbg[7] += 1;   // force the loads to be complete here
-                            long long c_b = clock64();
-                            if (wid == 0) t2_dbg[0] += c_b - c_a;
-#endif
-                            if (t + 1 < t1) {
-                                int b2 = b, j2 = jt + 1;
-                                if (j2 >= ntile) { j2 = 0; ++b2; }
-                                load_tile(b2, j2, nxt);
-                            }
-#ifdef T2_TIMING
-                            long long c_c = clock64();
-                            if (wid == 0) t2_dbg[1] += c_c - c_b;
-#endif
+                            for (int q = 0; q < RB; ++q) { av[q] = n1[q]; n1[q] = n2[q]; }
+                            advance(b2, j2);
+                            if (t + 2 < t1) load_tile(b2, j2, n2);
                             const int c0 = base + 32 * jt, c = c0 + lane;
                             if (c0 + 31 <= r0) {  // no diagonal element in this tile
                                 const double vc = v[c];
                                 double ca[4] = {0.0, 0.0, 0.0, 0.0};   // four chains: FP64 dependent-issue latency is long
 #pragma unroll
-                                for (int q = 0; q < T2_RB; ++q) {
+                                for (int q = 0; q < RB; ++q) {
                                     ca[q & 3] = fma(av[q], vr[q], ca[q & 3]);
                                     rowp[q] = fma(av[q], vc, rowp[q]);
                                 }
@@ -186,7 +214,7 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                                 const double vc = cact ? v[c] : 0.0;
                                 double ca[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                                for (int q = 0; q < T2_RB; ++q) {
+                                for (int q = 0; q < RB; ++q) {
                                     ca[q & 3] = fma(av[q], vr[q], ca[q & 3]);
                                     rowp[q] = fma(av[q], (c != r0 + q) ? vc : 0.0, rowp[q]);  // diagonal counted once
                                 }
@@ -194,50 +222,16 @@ tridiag2_kernel(double* __restrict__ Aall, int N, double* __restrict__ dall, dou
                             }
                             if (jt == 0 && lane == 0) {  // column `base`: the next step's column
 #pragma unroll
-                                for (int q = 0; q < T2_RB; ++q)
+                                for (int q = 0; q < RB; ++q)
                                     if (r0 + q < N) colnext[r0 + q] = av[q];
                             }
-#ifdef T2_TIMING
-                            if (wid == 0) { t2_dbg[2] += clock64() - c_c; t2_dbg[3] += 1; }
-#endif
                         }
-#ifdef T2_TIMING
-                        long long c_r = clock64();
-#endif
                         __syncwarp();
-                        // halving butterfly: 16 row sums over 32 lanes in 16 shuffles; lane L ends with row L >> 1
-                        double r8[8], r4[4], r2[2], r1;
-                        const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const double send = u16 ? rowp[q] : rowp[q + 8];
-                            const double keep = u16 ? rowp[q + 8] : rowp[q];
-                            r8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const double send = u8 ? r8[q] : r8[q + 4];
-                            const double keep = u8 ? r8[q + 4] : r8[q];
-                            r4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const double send = u4 ? r4[q] : r4[q + 2];
-                            const double keep = u4 ? r4[q + 2] : r4[q];
-                            r2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-                        {
-                            const double send = u2 ? r2[0] : r2[1];
-                            const double keep = u2 ? r2[1] : r2[0];
-                            r1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                        }
-                        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
-                        const int rr = r0 + (lane >> 1);
-                        if (!(lane & 1) && rr < N) yp[rr] += r1;
+                        const double rsum = t2_row_reduce<RB>(rowp, lane);
+                        constexpr int G = 32 / RB;
+                        const int rr = r0 + lane / G;
+                        if ((lane % G) == 0 && rr < N) yp[rr] += rsum;
                         __syncwarp();
-#ifdef T2_TIMING
-                        if (wid == 0) { t2_dbg[4] += clock64() - c_r; t2_dbg[5] += 1; }
-#endif
                         ++b;
                         jt = 0;
                     }
@@ -364,11 +358,11 @@ static size_t t2_smem(int N) {
     return ((size_t)(2 * NB + 3 + NW) * N + 2 * NB + 32 ) * sizeof(double);
 }
 
-template <int NB, int NW>
+template <int NB, int NW, int RB>
 static int t2_launch(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau) {
     const size_t smem = t2_smem<NB, NW>(ctx->N);
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag2_kernel<NB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tridiag2_kernel<NB, NW><<<S, NW * 32, smem, ctx->stream>>>(A, ctx->N, d, e, tau);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(tridiag2_kernel<NB, NW, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tridiag2_kernel<NB, NW, RB><<<S, NW * 32, smem, ctx->stream>>>(A, ctx->N, d, e, tau);
     return 1;
 }
 
@@ -376,7 +370,9 @@ static int t2_launch(mcosb_ctx* ctx, int S, double* A, double* d, double* e, dou
 int mcosb_launch_tridiag2(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau) {
     const int N = ctx->N;
     if (N < 96) return 0;  // small matrices: the fused v1 kernel is already cheap and has less fixed overhead
-    // 8 warps + panels of 8 keep the footprint at 27 N doubles: two matrices per SM up to N ~ 520, one beyond
-    if (t2_smem<8, 8>(N) <= (size_t)ctx->smem_optin) return t2_launch<8, 8>(ctx, S, A, d, e, tau);
+    // measured on B200 at N = 500 (scratch/t2_time.cu): 16 warps x 8-row tiles 13.4 ms per 148 matrices, 8 warps x
+    // 16-row tiles 13.7 ms; the smaller footprint (27 N doubles) carries N up to ~1050
+    if (t2_smem<8, 16>(N) <= (size_t)ctx->smem_optin) return t2_launch<8, 16, 8>(ctx, S, A, d, e, tau);
+    if (t2_smem<8, 8>(N) <= (size_t)ctx->smem_optin) return t2_launch<8, 8, 16>(ctx, S, A, d, e, tau);
     return 0;
 }
