@@ -63,6 +63,9 @@ def kernel_models(n, t):
         "eigvals": ("fp64", 2.0 * 2 * 64 * n * n, "flop"),                # 64 bisection steps x N-step Sturm recurrence
         "mpfit": ("fp64", 11 * 1000.0 * n * 25, "flop"),                  # ~11 objective passes x 1000 x N exp (~25 flop)
         "eigvec": ("hbm", 3 * 8.0 * n * n, "B"),                          # reflectors read + cov written and rescaled
+        "inviter": ("hbm", 8 * 5 * 8.0 * n * 10, "B"),                    # ~8 passes over 5 N-vectors for ~10 eigenvectors
+        "backtransform": ("hbm", 8.0 * n * n / 2, "B"),                   # reflectors read once (shared by the vectors via L1/L2)
+        "reconstruct": ("hbm", 8.0 * n * n, "B"),                         # de-noised covariance written once
         "markowitz": ("hbm", 8.0 * n * 50 * 60, "B"),                     # ~60 iterations x |F|~50 rows of C from L2
         "hrp_dist": ("hbm", 16.0 * n * n, "B"),
         "hrp_euclid": ("fp64_nofma", 3.0 * n3 / 2, "instr"),              # sub, mul, add per (i<j, k): bit-exact, no FMA

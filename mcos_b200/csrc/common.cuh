@@ -48,6 +48,9 @@ enum KernelId {
     MK_TRIDIAG2,
     MK_HRP_PERMUTE,
     MK_HRP_BISECT,
+    MK_INVITER,
+    MK_BACKTRANSFORM,
+    MK_RECONSTRUCT,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -74,7 +77,10 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "nco_alloc",
     "tridiag2",
     "hrp_permute",
-    "hrp_bisect"
+    "hrp_bisect",
+    "inviter",
+    "backtransform",
+    "reconstruct"
 };
 
 struct mcosb_ctx {

@@ -13,6 +13,8 @@
 #include "common.cuh"
 
 int mcosb_launch_tridiag2(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau);
+int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d, const double* e, const double* tau,
+                         const double* lam, const int* nf, const double* sigma, double* cov, int* status);
 
 // ---------------------------------------------------------------------------------------------------------------
 // D1: correlation matrix.  grid = (ceil(N/8), S), 256 threads, one warp per row.
@@ -573,7 +575,9 @@ __global__ void __launch_bounds__(VC_THREADS) eigvec_kernel(const double* __rest
                                                             const double* __restrict__ sigmaall,
                                                             double* __restrict__ workall,  // [S][5][N][VC_VCH]
                                                             unsigned char* __restrict__ pivall,  // [S][N][VC_VCH]
-                                                            double* __restrict__ covall, int* __restrict__ status) {
+                                                            double* __restrict__ covall, int* __restrict__ status,
+                                                            int skip_upto) {
+    if (nfall[blockIdx.x] <= skip_upto) return;  // handled by the wide path (eigvec3.cu)
     extern __shared__ double sm[];
     double* sd = sm;                  // [N]
     double* se = sd + N;              // [N]
@@ -735,16 +739,13 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     if (n_obs < 1 || !(bandwidth > 0.0)) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad n_obs/bandwidth");
     const int N = ctx->N;
     const size_t n = (size_t)N;
-    double *A, *sigma, *d, *e, *tau, *lam, *work;
-    unsigned char* piv;
+    double *A, *sigma, *d, *e, *tau, *lam;
     int* nf;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_A, (size_t)S * n * n, &A));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_SIGMA, (size_t)S * n, &sigma));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_D, (size_t)S * n, &d));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_E, (size_t)S * n, &e));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_TAU, (size_t)S * n, &tau));
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_WORK, (size_t)S * 5 * n * VC_VCH, &work));
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_VEC, (size_t)S * n * VC_VCH, &piv));
     lam = deig;
     if (!lam) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_LAM, (size_t)S * n, &lam));
     nf = dnf;
@@ -774,11 +775,21 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     mpfit_kernel<<<S, MP_THREADS, smem_mp, ctx->stream>>>(lam, N, q, bandwidth, dvar, nf, dstatus);
     MCOSB_LAUNCHED(ctx, MK_MPFIT);
 
-    size_t smem_vc = (2 * n + (size_t)VC_VCH * n + VC_VCH) * sizeof(double);
-    if (smem_vc > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for eigvec_kernel");
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vc));
-    eigvec_kernel<<<S, VC_THREADS, smem_vc, ctx->stream>>>(A, N, d, e, tau, lam, nf, sigma, work, piv, dcov, dstatus);
-    MCOSB_LAUNCHED(ctx, MK_EIGVEC);
+    // wide path (eigvec3.cu) for simulations with at most 16 signal eigenvalues; eigvec_kernel takes the others
+    int rv = mcosb_launch_eigvec3(ctx, S, A, d, e, tau, lam, nf, sigma, dcov, dstatus);
+    if (rv < 0) return rv;
+    {
+        double* work2;
+        unsigned char* piv2;
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_MK_L, (size_t)S * 5 * n * VC_VCH, &work2));
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_MK_W, (size_t)S * n * VC_VCH, &piv2));
+        size_t smem_vc = (2 * n + (size_t)VC_VCH * n + VC_VCH) * sizeof(double);
+        if (smem_vc > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for eigvec_kernel");
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vc));
+        eigvec_kernel<<<S, VC_THREADS, smem_vc, ctx->stream>>>(A, N, d, e, tau, lam, nf, sigma, work2, piv2, dcov, dstatus,
+                                                              rv == 1 ? 16 : -1);
+        MCOSB_LAUNCHED(ctx, MK_EIGVEC);
+    }
     return MCOSB_OK;
 }
 

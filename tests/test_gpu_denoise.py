@@ -72,3 +72,23 @@ def test_denoise_identity_and_constant_inputs():
         d = oracle.denoise_details(c, t)
         assert int(info["n_facts"][i]) == d["n_facts"]
         assert_allclose(out[i], d["cov"], rtol=1e-6, atol=1e-12)
+
+
+def test_denoise_many_signal_eigenvalues_and_mixed_batch():
+    """More than 16 signal eigenvalues takes the one-CTA-per-matrix eigenvector kernel, fewer the wide kernels; a batch
+    that mixes both must give every simulation the right answer."""
+    n, t = 80, 400
+    rng = np.random.RandomState(4)
+    load = rng.standard_normal((n, 24)) * 1.5
+    strong = load @ load.T + np.eye(n)                       # 24 strong factors -> n_facts > 16
+    mu, weak = block_diagonal_truth(80, n_blocks=4)          # 4 factors
+    weak = weak / weak.max()
+    covs = []
+    for base in (strong, weak, strong, weak, weak):
+        covs.append(np.cov(rng.multivariate_normal(np.zeros(n), base, size=t), rowvar=False))
+    covs = np.stack(covs)
+    eng = Engine(n, t)
+    out, info = eng.denoise(covs, t)
+    assert info["n_facts"].max() > 16 and info["n_facts"].min() <= 16
+    for i in range(len(covs)):
+        _check(covs[i], t, out, info, i)
