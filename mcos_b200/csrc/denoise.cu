@@ -313,31 +313,78 @@ struct MPCtx {
     double* red;
 };
 
+// Objective and analytic derivative at v.  The Gaussian kernel sums over a UNIFORM grid obey a two-multiply recurrence:
+//   g_k = exp(-(x_k - lam)^2 / 2h^2),  g_{k+1} = g_k r_k,  r_{k+1} = r_k c,  c = exp(-dx^2 / h^2),
+// so a thread that owns MP_KB consecutive grid points pays two exp per eigenvalue instead of MP_KB.  Thread layout:
+// MP_IG threads share one block of MP_KB grid points and split the eigenvalues between them (reduced with shuffles).
+// 1000 points = 63 blocks of 16 x 8 eigenvalue groups = 504 active threads.
+#define MP_KB 16
+#define MP_IG 8
 __device__ void mp_eval(const MPCtx& c, double v, double& f, double& g) {
     const double sq = sqrt(1.0 / c.q);
     const double lo = v * (1.0 - sq) * (1.0 - sq), hi = v * (1.0 + sq) * (1.0 + sq);
     const double step = (hi - lo) / (MP_PTS - 1);
+    const int kb = threadIdx.x / MP_IG, ig = threadIdx.x % MP_IG;
+    const int k0 = kb * MP_KB;
     double fs = 0.0, gs = 0.0;
-    for (int k = threadIdx.x; k < MP_PTS; k += MP_THREADS) {
-        // numpy.linspace: arange * step + start (two roundings, no FMA), last point forced to the stop value
-        const double x = (k == MP_PTS - 1) ? hi : __dadd_rn(__dmul_rn((double)k, step), lo);
-        const double rad = fmax((hi - x) * (x - lo), 0.0);
-        const double pdf = c.q / (2.0 * M_PI * v * x) * sqrt(rad);
-        double ks = 0.0, kd = 0.0;
-        for (int i = 0; i < c.N; ++i) {
-            double dif = x - c.lam[i];
-            double E = exp(-dif * dif * c.inv2h2);
-            ks += E;
-            kd = fma(E, dif, kd);
+    {   // all 512 threads run the loop (the shuffles need full warps); the last group's points are past the grid
+        double s0[MP_KB], sl[MP_KB];
+#pragma unroll
+        for (int j = 0; j < MP_KB; ++j) s0[j] = sl[j] = 0.0;
+        const double x0 = __dadd_rn(__dmul_rn((double)k0, step), lo);
+        const double cstep = exp(-step * step * c.invh2);
+        for (int i = ig; i < c.N; i += MP_IG) {
+            const double lam = c.lam[i];
+            const double d0 = x0 - lam;
+            double gk = exp(-d0 * d0 * c.inv2h2);
+            if (gk == 0.0) continue;                       // the whole block is below 1e-323 for this eigenvalue
+            double rk = exp(-(2.0 * d0 * step + step * step) * c.inv2h2);
+            if (!(rk < 1e150)) {                           // pathological bandwidth: direct evaluation
+#pragma unroll
+                for (int j = 0; j < MP_KB; ++j) {
+                    const double dj = d0 + j * step;
+                    const double E = exp(-dj * dj * c.inv2h2);
+                    s0[j] += E;
+                    sl[j] = fma(E, lam, sl[j]);
+                }
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < MP_KB; ++j) {
+                s0[j] += gk;
+                sl[j] = fma(gk, lam, sl[j]);
+                gk *= rk;
+                rk *= cstep;
+            }
         }
-        const double kde = c.cnorm * ks;
-        const double dkde = -c.cnorm * kd * c.invh2 * (x / v);
-        const double r = kde - pdf;
-#ifdef MCOSB_DEBUG_MPFIT
-        if (!isfinite(r) || !isfinite(dkde)) printf("nan at k=%d x=%.17g lo=%.17g hi=%.17g rad=%.17g pdf=%.17g kde=%.17g dkde=%.17g v=%.17g\n", k, x, lo, hi, rad, pdf, kde, dkde, v);
-#endif
-        fs = fma(r, r, fs);
-        gs = fma(2.0 * r, dkde + pdf / v, gs);
+        // reduce over the MP_IG threads of the group (adjacent lanes)
+#pragma unroll
+        for (int j = 0; j < MP_KB; ++j) {
+#pragma unroll
+            for (int o = MP_IG / 2; o > 0; o >>= 1) {
+                s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], o);
+                sl[j] += __shfl_xor_sync(0xffffffffu, sl[j], o);
+            }
+        }
+        // each thread of the group finishes MP_KB / MP_IG of the block's grid points
+#pragma unroll
+        for (int j = 0; j < MP_KB; ++j) {
+            if ((j % MP_IG) == ig) {
+                const int k = k0 + j;
+                if (k < MP_PTS) {
+                    // numpy.linspace: arange * step + start (two roundings, no FMA), last point forced to the stop value
+                    const double x = (k == MP_PTS - 1) ? hi : __dadd_rn(__dmul_rn((double)k, step), lo);
+                    const double rad = fmax((hi - x) * (x - lo), 0.0);
+                    const double pdf = c.q / (2.0 * M_PI * v * x) * sqrt(rad);
+                    const double kde = c.cnorm * s0[j];
+                    const double kd = x * s0[j] - sl[j];                 // sum_i E_i (x - lam_i)
+                    const double dkde = -c.cnorm * kd * c.invh2 * (x / v);
+                    const double r = kde - pdf;
+                    fs = fma(r, r, fs);
+                    gs = fma(2.0 * r, dkde + pdf / v, gs);
+                }
+            }
+        }
     }
     f = block_sum(fs, c.red);
     g = block_sum(gs, c.red);

@@ -77,11 +77,13 @@ def test_denoise_identity_and_constant_inputs():
 def test_denoise_many_signal_eigenvalues_and_mixed_batch():
     """More than 16 signal eigenvalues takes the one-CTA-per-matrix eigenvector kernel, fewer the wide kernels; a batch
     that mixes both must give every simulation the right answer."""
-    n, t = 80, 400
+    n, t = 120, 1200
     rng = np.random.RandomState(4)
-    load = rng.standard_normal((n, 24)) * 1.5
-    strong = load @ load.T + np.eye(n)                       # 24 strong factors -> n_facts > 16
-    mu, weak = block_diagonal_truth(80, n_blocks=4)          # 4 factors
+    load = np.zeros((n, 30))
+    for f in range(30):
+        load[4 * f:4 * f + 4, f] = 3.0                         # 30 blocks of 4 tightly tied assets -> n_facts = 30
+    strong = load @ load.T + np.eye(n)
+    mu, weak = block_diagonal_truth(120, n_blocks=4)           # 4 factors
     weak = weak / weak.max()
     covs = []
     for base in (strong, weak, strong, weak, weak):
