@@ -51,8 +51,8 @@ enum {
 enum { MCOSB_MOMENTS_MUCOV = 0, MCOSB_MOMENTS_LEDOIT_WOLF = 1, MCOSB_MOMENTS_JACKKNIFE = 2 };
 /* error estimators: error_estimator.py:21-25 / 28-32 / 35-41 */
 enum { MCOSB_ERR_EXPECTED_OUTCOME = 0, MCOSB_ERR_VARIANCE = 1, MCOSB_ERR_SHARPE = 2 };
-/* optimizers for mcosb_run: optimizer.py:41-53 / 198-287 / 56-195 */
-enum { MCOSB_OPT_MARKOWITZ = 0, MCOSB_OPT_HRP = 1, MCOSB_OPT_NCO = 2 };
+/* optimizers for mcosb_run: optimizer.py:41-53 / 198-287 / 56-195 / 290-359 (equal risk budget) */
+enum { MCOSB_OPT_MARKOWITZ = 0, MCOSB_OPT_HRP = 1, MCOSB_OPT_NCO = 2, MCOSB_OPT_RISK_PARITY = 3 };
 
 int mcosb_version(void);
 
@@ -86,6 +86,11 @@ int mcosb_moments(mcosb_ctx* ctx, int S, const double* X, int kind, double* mu_h
 int mcosb_denoise(mcosb_ctx* ctx, int S, double* cov_inout, int n_obs, double bandwidth, double* eigvals, double* var,
                   int* n_facts, int* status);
 
+/* DetoneCovarianceTransformer.transform (covariance_transformer.py:222-250), in place on cov[S][N][N]: removes the
+ * n_remove (0..16) largest eigen-components of the correlation matrix, renormalises it to unit diagonal and rescales by
+ * the input standard deviations.  n_remove == 0 leaves cov untouched.  status[S] nullable. */
+int mcosb_detone(mcosb_ctx* ctx, int S, double* cov_inout, int n_remove, int* status);
+
 /* MarkowitzOptimizer.allocate (optimizer.py:44-49 + PyPortfolioOpt 0.5.2 max_sharpe): long-only max-Sharpe weights
  * w[S][N] by an exact active-set QP.  clean != 0 applies clean_weights (|w| < 1e-4 -> 0, round to 5 decimals).
  * Nullable: iters[S], status[S]. */
@@ -101,6 +106,13 @@ int mcosb_hrp(mcosb_ctx* ctx, int S, const double* cov, double* w, int* order, d
  * Nullable: labels_out[S][N], status[S]. */
 int mcosb_nco(mcosb_ctx* ctx, int S, const double* mu, const double* cov, int max_clusters, int trials,
               const int* labels_in, double* w, int* labels_out, int* status);
+
+/* RiskParityOptimizer.allocate (optimizer.py:298-359).  budget[N] nullable (equal risk budget 1/N).  Returns the
+ * budget itself when SLSQP's first convergence test would fire at it (as the reference does on covariances of
+ * realistic scale), otherwise the exact risk-budgeting weights (Newton on Spinu's convex formulation).
+ * Nullable: iters[S] (0 = returned at the starting point), status[S]. */
+int mcosb_risk_parity(mcosb_ctx* ctx, int S, const double* cov, const double* budget, double* w, int* iters,
+                      int* status);
 
 /* AbstractErrorEstimator.estimate against the TRUE (mu, cov) set by mcosb_set_truth (error_estimator.py:21-49).
  * w[S][N]; w_star is [S][N] if w_star_batched else [N] (the loop-invariant ideal allocation, mcos.py:30). */
@@ -119,6 +131,7 @@ typedef struct mcosb_plan {
     int nco_max_clusters;    /* NCO: 0 = N/2 */
     int nco_trials;          /* NCO: num_clustering_trials */
     int wave;                /* simulations per wave (0 = choose from free memory) */
+    int detone_n_remove;     /* > 0: apply DetoneCovarianceTransformer(n_remove) after the DeNoiser */
 } mcosb_plan;
 
 /* err[S][n_optimizers]; status[S] nullable.  The ideal allocations (optimizer.allocate(true mu, true cov)) are

@@ -14,7 +14,7 @@ STAGE_NAMES = ("sample", "moments", "denoise", "markowitz", "hrp", "nco", "error
 
 MOMENTS_MUCOV, MOMENTS_LEDOIT_WOLF, MOMENTS_JACKKNIFE = 0, 1, 2
 ERR_EXPECTED_OUTCOME, ERR_VARIANCE, ERR_SHARPE = 0, 1, 2
-OPT_MARKOWITZ, OPT_HRP, OPT_NCO = 0, 1, 2
+OPT_MARKOWITZ, OPT_HRP, OPT_NCO, OPT_RISK_PARITY = 0, 1, 2, 3
 
 ST_NOT_PD, ST_NO_EXCESS, ST_QP_CAP, ST_MPFIT_FAIL, ST_EIGVEC, ST_HRP_SUM, ST_NONFINITE = 1, 2, 4, 8, 16, 32, 64
 
@@ -26,7 +26,7 @@ class MCOSBError(RuntimeError):
 class Plan(ctypes.Structure):
     _fields_ = [("moments_kind", c_int), ("denoise", c_int), ("bandwidth", c_double), ("n_optimizers", c_int),
                 ("optimizers", c_int * 4), ("error_kind", c_int), ("risk_free_rate", c_double),
-                ("nco_max_clusters", c_int), ("nco_trials", c_int), ("wave", c_int)]
+                ("nco_max_clusters", c_int), ("nco_trials", c_int), ("wave", c_int), ("detone_n_remove", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/mcosb.h declares
@@ -41,9 +41,11 @@ SIGNATURES = {
     "mcosb_sample": (c_int, [c_void_p, c_uint64, c_int, c_void_p]),
     "mcosb_moments": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mcosb_denoise": (c_int, [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcosb_detone": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "mcosb_markowitz": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "mcosb_hrp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_nco": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcosb_risk_parity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_errors": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mcosb_run": (c_int, [c_void_p, POINTER(Plan), c_uint64, c_int, c_void_p, c_void_p]),
     "mcosb_last_stage_ms": (c_int, [c_void_p, POINTER(c_double)]),

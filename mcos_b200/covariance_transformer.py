@@ -46,14 +46,22 @@ class DeNoiserCovarianceTransformer(AbstractCovarianceTransformer):
 
 
 class DetoneCovarianceTransformer(AbstractCovarianceTransformer):
-    """Removes the n_remove largest eigen-components (mcos/covariance_transformer.py:211-250).
-    Not on the north-star hot path (SURVEY 8f "next"); no GPU kernel yet and, by design, no CPU fallback."""
+    """Removes the n_remove largest eigen-components of the correlation matrix -- the "market" factors -- renormalises
+    and rescales (mcos/covariance_transformer.py:211-250).  GPU: shared eigen front end + detone_kernel; n_remove <= 16."""
 
-    def __init__(self, n_remove: int):
+    def __init__(self, n_remove: int, *, device: int = 0):
         self.n_remove = n_remove
+        self.device = device
 
     def transform(self, cov: np.array, n_observations: int) -> np.array:
         if self.n_remove == 0:
             return cov
-        raise NotImplementedError("DetoneCovarianceTransformer has no GPU kernel yet (SURVEY.md 8f); "
-                                  "there is no CPU fallback")
+        return self.transform_batch(np.asarray(cov, dtype=np.float64)[None])[0]
+
+    def transform_batch(self, cov):
+        cov = np.asarray(cov, dtype=np.float64)
+        if self.n_remove == 0:
+            return cov
+        eng = get_engine(cov.shape[1], 1, self.device)
+        out, _ = eng.detone(cov, self.n_remove)
+        return out

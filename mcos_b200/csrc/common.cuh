@@ -51,6 +51,8 @@ enum KernelId {
     MK_INVITER,
     MK_BACKTRANSFORM,
     MK_RECONSTRUCT,
+    MK_DETONE,
+    MK_RISK_PARITY,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -80,7 +82,9 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "hrp_bisect",
     "inviter",
     "backtransform",
-    "reconstruct"
+    "reconstruct",
+    "detone",
+    "risk_parity"
 };
 
 struct mcosb_ctx {
@@ -280,6 +284,11 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX);
 int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink);
 int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
                       int* dnf, int* dstatus);
+int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, double* sigma, double* d, double* e,
+                          double* tau, double* lam);
+int mcosb_dev_detone(mcosb_ctx* ctx, int S, double* dcov, int n_remove, int* dstatus);
+int mcosb_dev_risk_parity(mcosb_ctx* ctx, int S, const double* dcov, const double* dbudget, double* dw, int* diters,
+                          int* dstatus);
 int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, double rf, int clean,
                         double* dw, int* diters, int* dstatus);
 int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* dorder, double* dlink, int* dstatus);

@@ -780,23 +780,12 @@ __global__ void __launch_bounds__(VC_THREADS) eigvec_kernel(const double* __rest
     if (status && __syncthreads_or(bad_vec) && tid == 0) atomicOr(&status[s], MCOSB_ST_EIGVEC);
 }
 
-int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
-                      int* dnf, int* dstatus) {
-    if (S == 0) return MCOSB_OK;
-    if (n_obs < 1 || !(bandwidth > 0.0)) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad n_obs/bandwidth");
+// corr = cov_to_corr(cov) -> Householder tridiagonalisation (reflectors left in A) -> all eigenvalues, descending.
+// Shared by the DeNoiser and the Detone transformer.
+int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, double* sigma, double* d, double* e,
+                          double* tau, double* lam) {
     const int N = ctx->N;
     const size_t n = (size_t)N;
-    double *A, *sigma, *d, *e, *tau, *lam;
-    int* nf;
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_A, (size_t)S * n * n, &A));
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_SIGMA, (size_t)S * n, &sigma));
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_D, (size_t)S * n, &d));
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_E, (size_t)S * n, &e));
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_TAU, (size_t)S * n, &tau));
-    lam = deig;
-    if (!lam) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_LAM, (size_t)S * n, &lam));
-    nf = dnf;
-    if (!nf) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_NF, (size_t)S, &nf));
     corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
     MCOSB_LAUNCHED(ctx, MK_CORR);
 
@@ -815,6 +804,27 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ev));
     eigvals_kernel<<<S, EV_THREADS, smem_ev, ctx->stream>>>(d, e, N, lam);
     MCOSB_LAUNCHED(ctx, MK_EIGVALS);
+    return MCOSB_OK;
+}
+
+int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
+                      int* dnf, int* dstatus) {
+    if (S == 0) return MCOSB_OK;
+    if (n_obs < 1 || !(bandwidth > 0.0)) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad n_obs/bandwidth");
+    const int N = ctx->N;
+    const size_t n = (size_t)N;
+    double *A, *sigma, *d, *e, *tau, *lam;
+    int* nf;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_A, (size_t)S * n * n, &A));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_SIGMA, (size_t)S * n, &sigma));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_D, (size_t)S * n, &d));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_E, (size_t)S * n, &e));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_TAU, (size_t)S * n, &tau));
+    lam = deig;
+    if (!lam) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_LAM, (size_t)S * n, &lam));
+    nf = dnf;
+    if (!nf) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_NF, (size_t)S, &nf));
+    MCOSB_TRY(mcosb_dev_eig_prepare(ctx, S, dcov, A, sigma, d, e, tau, lam));
 
     const double q = (double)n_obs / (double)N;
     size_t smem_mp = n * sizeof(double);

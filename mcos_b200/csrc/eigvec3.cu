@@ -238,3 +238,101 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
     MCOSB_LAUNCHED(ctx, MK_RECONSTRUCT);
     return 1;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// DetoneCovarianceTransformer.transform (covariance_transformer.py:222-250): remove the n_remove largest
+// eigen-components of the correlation matrix, renormalise to unit diagonal, rescale by the input standard deviations.
+// Reuses the eigen front end and the wide eigenvector kernels with n_facts := n_remove for every simulation.
+// (The reference sorts eigenvalues by absolute value; for a positive semi-definite correlation matrix that is the same
+// order.  corr_ii is taken as exactly 1; the reference's value is within one ulp of it.)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void fill_int_kernel(int* p, size_t n, int v) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// grid = (ceil(N / 8), S), one warp per row, in place on cov (each element is read before it is overwritten)
+__global__ void __launch_bounds__(256) detone_kernel(const double* __restrict__ V, const double* __restrict__ lamall,
+                                                     int n_remove, const double* __restrict__ sigmaall, int N,
+                                                     double* __restrict__ covall) {
+    extern __shared__ double sm[];
+    double* rs = sm;             // [N] sqrt(diag(c2))
+    const int sim = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double* lam = lamall + (size_t)sim * N;
+    const double* sigma = sigmaall + (size_t)sim * N;
+    const double* Vs = V + (size_t)sim * EV3_VMAX * N;
+    for (int j = tid; j < N; j += 256) {
+        double r = 1.0;
+        for (int s = 0; s < n_remove; ++s) { const double v = Vs[(size_t)s * N + j]; r = fma(-lam[s] * v, v, r); }
+        rs[j] = sqrt(r);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 8 + wid;
+    if (i >= N) return;
+    double vi[EV3_VMAX];
+#pragma unroll
+    for (int s = 0; s < EV3_VMAX; ++s) vi[s] = (s < n_remove) ? lam[s] * Vs[(size_t)s * N + i] : 0.0;
+    const double rsi = rs[i], si = sigma[i];
+    double* row = covall + (size_t)sim * N * N + (size_t)i * N;
+    for (int j = lane; j < N; j += 32) {
+        const double sj = sigma[j];
+        double c = row[j] / (si * sj);
+        c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+        if (i == j) c = 1.0;
+#pragma unroll
+        for (int s = 0; s < EV3_VMAX; ++s)
+            if (s < n_remove) c = fma(-vi[s], Vs[(size_t)s * N + j], c);
+        row[j] = (c / (rsi * rs[j])) * (si * sj);
+    }
+}
+
+int mcosb_dev_detone(mcosb_ctx* ctx, int S, double* dcov, int n_remove, int* dstatus) {
+    if (S == 0 || n_remove == 0) return MCOSB_OK;   // n_remove == 0 returns the input (covariance_transformer.py:223-224)
+    const int N = ctx->N;
+    const size_t n = (size_t)N;
+    if (n_remove < 0 || n_remove > EV3_VMAX || n_remove > N)
+        return mcosb_fail(ctx, MCOSB_ERR_ARG, "detone: n_remove must be between 0 and min(16, n_assets)");
+    if (N > 1024) return mcosb_fail(ctx, MCOSB_ERR_ARG, "detone: n_assets too large");
+    double *A, *sigma, *d, *e, *tau, *lam, *W, *V;
+    unsigned char* piv;
+    int* nf;
+    const size_t G = (size_t)S * EV3_VMAX;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_A, (size_t)S * n * n, &A));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_SIGMA, (size_t)S * n, &sigma));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_D, (size_t)S * n, &d));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_E, (size_t)S * n, &e));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_TAU, (size_t)S * n, &tau));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_LAM, (size_t)S * n, &lam));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_NF, (size_t)S, &nf));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_WORK, 5 * n * G, &W));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_VEC, n * G, &piv));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_VAR, n * G, &V));
+    MCOSB_TRY(mcosb_dev_eig_prepare(ctx, S, dcov, A, sigma, d, e, tau, lam));
+    fill_int_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(nf, (size_t)S, n_remove);
+    MCOSB_LAUNCHED(ctx, MK_FILL);
+    inviter_kernel<<<(unsigned)((G + 63) / 64), 64, 0, ctx->stream>>>(d, e, lam, nf, N, S, W, piv);
+    MCOSB_LAUNCHED(ctx, MK_INVITER);
+    const unsigned bt_grid = (unsigned)((G + 7) / 8);
+    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
+    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
+    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
+    else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
+    MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
+    detone_kernel<<<dim3((N + 7) / 8, S), 256, n * sizeof(double), ctx->stream>>>(V, lam, n_remove, sigma, N, dcov);
+    MCOSB_LAUNCHED(ctx, MK_DETONE);
+    return MCOSB_OK;
+}
+
+extern "C" int mcosb_detone(mcosb_ctx* ctx, int S, double* cov_inout, int n_remove, int* status) {
+    MCOSB_CHECK_CTX(ctx);
+    if (S < 0 || !cov_inout) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_detone");
+    const size_t N = ctx->N;
+    Staging st(ctx);
+    double* dcov;
+    int* dst;
+    MCOSB_TRY(st.inout(cov_inout, (size_t)S * N * N, SL_STAGE_IN0, &dcov));
+    MCOSB_TRY(st.out(status, (size_t)S, SL_STAGE_OUT3, &dst));
+    if (dst) MCOSB_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)S * sizeof(int), ctx->stream));
+    MCOSB_TRY(mcosb_dev_detone(ctx, S, dcov, n_remove, dst));
+    return st.finish();
+}

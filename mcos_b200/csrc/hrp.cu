@@ -117,12 +117,11 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
     int* segB = segA + N + 1;       // [N+1]
     int* merged = segB + N + 1;     // [N]
     int* ired = merged + N;         // [32]
-    __shared__ int s_x, s_nseg;
+    __shared__ int s_x;
 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NW = TR_THREADS / 32;
     const double* E = Eall + (size_t)s * N * N;
-    const double* C = cov_all + (size_t)s * N * N;
 
     if (N == 1) {
         if (tid == 0) order_all[s] = 0;
@@ -204,8 +203,6 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
             if (node < N) order[pos++] = node;
             else { parent[sp++] = sb[node - N]; parent[sp++] = sa[node - N]; }
         }
-        segA[0] = 0; segA[1] = N;
-        s_nseg = 1;
     }
     __syncthreads();
     if (link_all) {

@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
     s.counts = s.lbest + N;
     s.ired = s.counts + max_k;
     __shared__ int s_flag, s_pick;
-    __shared__ double s_pot;
     const int sim = blockIdx.x, tid = threadIdx.x;
     const double* X = Dall + (size_t)sim * N * N;   // symmetric: X[d][i] == X[i][d]; threads read "columns" coalesced
     const double* E = Eall + (size_t)sim * N * N;

@@ -40,6 +40,11 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
         MCOSB_TRY(mcosb_dev_denoise(ctx, W, dcov, ctx->T, plan->bandwidth, nullptr, nullptr, nullptr, dstatus));
         MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, false));
     }
+    if (plan->detone_n_remove > 0) {
+        MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, true));
+        MCOSB_TRY(mcosb_dev_detone(ctx, W, dcov, plan->detone_n_remove, dstatus));
+        MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, false));
+    }
     double* dw;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_RUN_W, (size_t)W * N, &dw));
     for (int o = 0; o < plan->n_optimizers; ++o) {
@@ -53,6 +58,10 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
             stage = MCOSB_STAGE_HRP;
             MCOSB_TRY(mark(stage, true));
             MCOSB_TRY(mcosb_dev_hrp(ctx, W, dcov, dw, nullptr, nullptr, dstatus));
+        } else if (kind == MCOSB_OPT_RISK_PARITY) {
+            stage = MCOSB_STAGE_NCO;   // reported with the "other optimizers" stage timer
+            MCOSB_TRY(mark(stage, true));
+            MCOSB_TRY(mcosb_dev_risk_parity(ctx, W, dcov, nullptr, dw, nullptr, dstatus));
         } else {
             stage = MCOSB_STAGE_NCO;
             MCOSB_TRY(mark(stage, true));
@@ -74,8 +83,8 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
     if (plan->n_optimizers < 1 || plan->n_optimizers > 4) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_optimizers must be 1..4");
     for (int o = 0; o < plan->n_optimizers; ++o)
-        if (plan->optimizers[o] < 0 || plan->optimizers[o] > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown optimizer");
-    const size_t N = ctx->N, T = ctx->T;
+        if (plan->optimizers[o] < 0 || plan->optimizers[o] > 3) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown optimizer");
+    const size_t N = ctx->N;
     const int nopt = plan->n_optimizers;
     for (int i = 0; i < MCOSB_N_STAGES; ++i) ctx->stage_ms[i] = 0.0;
     if (S == 0) return MCOSB_OK;
@@ -102,6 +111,8 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
             MCOSB_TRY(mcosb_dev_markowitz(ctx, 1, ctx->d_mu, ctx->d_cov, plan->risk_free_rate, 1, wi, nullptr, d_ideal_status));
         else if (kind == MCOSB_OPT_HRP)
             MCOSB_TRY(mcosb_dev_hrp(ctx, 1, ctx->d_cov, wi, nullptr, nullptr, d_ideal_status));
+        else if (kind == MCOSB_OPT_RISK_PARITY)
+            MCOSB_TRY(mcosb_dev_risk_parity(ctx, 1, ctx->d_cov, nullptr, wi, nullptr, d_ideal_status));
         else
             MCOSB_TRY(mcosb_dev_nco(ctx, 1, ctx->d_mu, ctx->d_cov, plan->nco_max_clusters, plan->nco_trials, nullptr, wi,
                                     nullptr, d_ideal_status));

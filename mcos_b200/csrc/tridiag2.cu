@@ -369,7 +369,7 @@ static int t2_launch(mcosb_ctx* ctx, int S, double* A, double* d, double* e, dou
 // Returns 1 if launched, 0 if this size is not supported (caller falls back to tridiag_kernel), <0 on error.
 int mcosb_launch_tridiag2(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau) {
     const int N = ctx->N;
-    if (N < 96) return 0;  // small matrices: the fused v1 kernel is already cheap and has less fixed overhead
+    if (N < 200) return 0;  // small matrices: the fused v1 kernel is faster (1.3 vs 2.9 us per matrix at N = 100)
     // measured on B200 at N = 500 (scratch/t2_time.cu): 16 warps x 8-row tiles 13.4 ms per 148 matrices, 8 warps x
     // 16-row tiles 13.7 ms; the smaller footprint (27 N doubles) carries N up to ~1050
     if (t2_smem<8, 16>(N) <= (size_t)ctx->smem_optin) return t2_launch<8, 16, 8>(ctx, S, A, d, e, tau);

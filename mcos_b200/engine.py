@@ -146,6 +146,15 @@ class Engine:
         self._check(self.lib.mcosb_denoise(self.h, s, pc, t, float(bandwidth), pe, pv, pn, ps))
         return kc, {"eigvals": eig, "var": var, "n_facts": nf, "status": st}
 
+    def detone(self, cov, n_remove):
+        s = cov.shape[0]
+        tt = _is_torch(cov)
+        work = cov.clone() if tt else np.array(cov, dtype=np.float64, order="C", copy=True)
+        kc, pc = self._in(work, (s, self.N, self.N))
+        st, ps = self._out(tt, (s,), np.int32)
+        self._check(self.lib.mcosb_detone(self.h, s, pc, int(n_remove), ps))
+        return kc, {"status": st}
+
     def markowitz(self, mu, cov, rf=0.02, clean=True):
         s = cov.shape[0]
         tt = _is_torch(cov)
@@ -180,6 +189,17 @@ class Engine:
         max_k = 0 if max_num_clusters is None else int(max_num_clusters)
         self._check(self.lib.mcosb_nco(self.h, s, pm, pc, max_k, int(num_clustering_trials), plab, pw, plo, ps))
         return w, {"labels": lab, "status": st}
+
+    def risk_parity(self, cov, budget=None):
+        s = cov.shape[0]
+        tt = _is_torch(cov)
+        kc, pc = self._in(cov, (s, self.N, self.N))
+        kb, pb = self._in(budget, (self.N,))
+        w, pw = self._out(tt, (s, self.N))
+        it, pi = self._out(tt, (s,), np.int32)
+        st, ps = self._out(tt, (s,), np.int32)
+        self._check(self.lib.mcosb_risk_parity(self.h, s, pc, pb, pw, pi, ps))
+        return w, {"iters": it, "status": st}
 
     def errors(self, w, w_star, kind=_lib.ERR_VARIANCE):
         s = w.shape[0]

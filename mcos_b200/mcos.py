@@ -12,18 +12,20 @@ import numpy as np
 import pandas as pd
 
 from . import _lib
-from .covariance_transformer import AbstractCovarianceTransformer, DeNoiserCovarianceTransformer
+from .covariance_transformer import AbstractCovarianceTransformer, DeNoiserCovarianceTransformer, \
+    DetoneCovarianceTransformer
 from .engine import get_engine
 from .error_estimator import AbstractErrorEstimator, ExpectedOutcomeErrorEstimator, SharpeRatioErrorEstimator, \
     VarianceErrorEstimator
 from .observation_simulator import AbstractObservationSimulator, MuCovJackknifeObservationSimulator, \
     MuCovLedoitWolfObservationSimulator, MuCovObservationSimulator
-from .optimizer import AbstractOptimizer, HRPOptimizer, MarkowitzOptimizer, NCOOptimizer
+from .optimizer import AbstractOptimizer, HRPOptimizer, MarkowitzOptimizer, NCOOptimizer, RiskParityOptimizer
 from .utils import convert_price_history
 
 _SIM_KIND = {MuCovObservationSimulator: _lib.MOMENTS_MUCOV, MuCovLedoitWolfObservationSimulator: _lib.MOMENTS_LEDOIT_WOLF,
              MuCovJackknifeObservationSimulator: _lib.MOMENTS_JACKKNIFE}
-_OPT_KIND = {MarkowitzOptimizer: _lib.OPT_MARKOWITZ, HRPOptimizer: _lib.OPT_HRP, NCOOptimizer: _lib.OPT_NCO}
+_OPT_KIND = {MarkowitzOptimizer: _lib.OPT_MARKOWITZ, HRPOptimizer: _lib.OPT_HRP, NCOOptimizer: _lib.OPT_NCO,
+             RiskParityOptimizer: _lib.OPT_RISK_PARITY}
 _ERR_KIND = {ExpectedOutcomeErrorEstimator: _lib.ERR_EXPECTED_OUTCOME, VarianceErrorEstimator: _lib.ERR_VARIANCE,
              SharpeRatioErrorEstimator: _lib.ERR_SHARPE}
 
@@ -44,14 +46,18 @@ def build_plan(obs_simulator, optimizers, error_estimator, covariance_transforme
         raise TypeError(f"no GPU stage for error estimator {type(error_estimator).__name__}")
     plan = _lib.Plan()
     plan.moments_kind = _SIM_KIND[type(obs_simulator)]
-    plan.denoise, plan.bandwidth = 0, 0.25
+    plan.denoise, plan.bandwidth, plan.detone_n_remove = 0, 0.25, 0
     for tr in covariance_transformers:
         if type(tr) is DeNoiserCovarianceTransformer:
-            if plan.denoise:
-                raise TypeError("at most one DeNoiserCovarianceTransformer is supported in a plan")
+            if plan.denoise or plan.detone_n_remove:
+                raise TypeError("the plan supports [DeNoiser], [Detone] or [DeNoiser, Detone], in that order")
             plan.denoise, plan.bandwidth = 1, float(tr.bandwidth)
-        elif getattr(tr, "n_remove", None) == 0:
-            continue  # Detone with n_remove = 0 is the identity (covariance_transformer.py:223-224)
+        elif type(tr) is DetoneCovarianceTransformer:
+            if tr.n_remove == 0:
+                continue  # the identity (covariance_transformer.py:223-224)
+            if plan.detone_n_remove:
+                raise TypeError("at most one DetoneCovarianceTransformer is supported in a plan")
+            plan.detone_n_remove = int(tr.n_remove)
         else:
             raise TypeError(f"no GPU stage for covariance transformer {type(tr).__name__}")
     if not 1 <= len(optimizers) <= 4:
@@ -62,6 +68,8 @@ def build_plan(obs_simulator, optimizers, error_estimator, covariance_transforme
         if type(opt) not in _OPT_KIND:
             raise TypeError(f"no GPU stage for optimizer {type(opt).__name__}")
         plan.optimizers[i] = _OPT_KIND[type(opt)]
+        if type(opt) is RiskParityOptimizer and opt.target_risk is not None:
+            raise TypeError("the fused loop supports RiskParityOptimizer with the default equal risk budget only")
         if type(opt) is NCOOptimizer:
             plan.nco_max_clusters = 0 if opt.max_num_clusters is None else int(opt.max_num_clusters)
             plan.nco_trials = int(opt.num_clustering_trials)

@@ -102,14 +102,23 @@ class NCOOptimizer(AbstractOptimizer):
 
 
 class RiskParityOptimizer(AbstractOptimizer):
-    """Risk parity (mcos/optimizer.py:290-359). Not on the north-star hot path (SURVEY 8f "next" #1); no GPU kernel yet
-    and, by design, no CPU fallback."""
+    """Risk parity / risk budgeting (mcos/optimizer.py:290-359).  The reference runs scipy SLSQP from the budget itself;
+    the GPU kernel returns the budget when SLSQP's first convergence test would fire there (what the reference does on
+    covariances of realistic scale) and the exact risk-budgeting weights otherwise (riskparity.cu)."""
 
-    def __init__(self, target_risk: np.array = None):
+    def __init__(self, target_risk: np.array = None, *, device: int = 0):
         self.target_risk = target_risk
+        self.device = device
 
     def allocate(self, mu: np.array, cov: np.array) -> np.array:
-        raise NotImplementedError("RiskParityOptimizer has no GPU kernel yet (SURVEY.md 8f); there is no CPU fallback")
+        return self.allocate_batch(cov)[0]
+
+    def allocate_batch(self, cov, return_details: bool = False):
+        _, cov, _ = _batch(None, cov)
+        eng = get_engine(cov.shape[1], 1, self.device)
+        budget = None if self.target_risk is None else np.asarray(self.target_risk, dtype=np.float64).reshape(-1)
+        w, info = eng.risk_parity(cov, budget)
+        return (w, info) if return_details else w
 
     @property
     def name(self) -> str:

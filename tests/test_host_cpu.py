@@ -72,10 +72,16 @@ def test_build_plan_maps_plugins_and_rejects_unknown_types():
     assert list(plan.optimizers)[:3] == [_lib.OPT_MARKOWITZ, _lib.OPT_HRP, _lib.OPT_NCO] and plan.n_optimizers == 3
     assert plan.error_kind == _lib.ERR_SHARPE and plan.nco_max_clusters == 5 and plan.nco_trials == 3
     assert plan.risk_free_rate == 0.02
-    with pytest.raises(TypeError):
-        mb.build_plan(sim, [mb.RiskParityOptimizer()], mb.VarianceErrorEstimator(), [])
-    with pytest.raises(TypeError):
-        mb.build_plan(sim, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [mb.DetoneCovarianceTransformer(1)])
+    assert list(mb.build_plan(sim, [mb.RiskParityOptimizer()], mb.VarianceErrorEstimator(), []).optimizers)[0] == \
+        _lib.OPT_RISK_PARITY
+    with pytest.raises(TypeError):   # custom budgets only through the optimizer object itself
+        mb.build_plan(sim, [mb.RiskParityOptimizer(np.full(4, .25))], mb.VarianceErrorEstimator(), [])
+    plan2 = mb.build_plan(sim, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(),
+                          [mb.DeNoiserCovarianceTransformer(), mb.DetoneCovarianceTransformer(2)])
+    assert plan2.denoise == 1 and plan2.detone_n_remove == 2
+    with pytest.raises(TypeError):   # the fused plan applies the DeNoiser first
+        mb.build_plan(sim, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(),
+                      [mb.DetoneCovarianceTransformer(1), mb.DeNoiserCovarianceTransformer()])
     with pytest.raises(TypeError):
         mb.build_plan(object(), [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [])
 
