@@ -317,8 +317,17 @@ def run_native(args):
         v["share"] = round(v["ms"] / tot, 4)
     top = max(table, key=lambda k: table[k]["ms"])
     tv = table[top]
+    traffic = None   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "tridiag2_traffic_r01.json")))
+        if top == "tridiag2" and tr["n_assets"] == N_ASSETS:
+            traffic = tr["dram_bytes_per_matrix"] * spp
+    except Exception:
+        pass
     roofline = {"kernel": top + "_kernel", "bound": tv["bound"] if tv["bound"] in ("hbm", "tensor") else "fp64",
-                "achieved": tv["achieved"], "peak": tv["peak"], "unit": tv["unit"], "frac": tv["frac"], "traffic": None,
+                "achieved": tv["achieved"], "peak": tv["peak"], "unit": tv["unit"], "frac": tv["frac"], "traffic": traffic,
+                "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per matrix (profiles/kernels_final_r01.md) x "
+                                "matrices per launch; algorithmic minimum is 12 N^2 bytes per matrix (3 MB)",
                 "share_of_step": tv["share"], "ms_per_launch": tv["ms"] / tv["launches"],
                 "peak_source": ("MEASURED_PEAKS.json (%s)" % hbm_src) if tv["bound"] == "hbm"
                 else "profiles/fp64_peaks_r01.json (measured on this pool; MEASURED_PEAKS.json has no FP64 entry)"}

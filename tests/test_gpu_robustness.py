@@ -1,0 +1,83 @@
+"""GPU: per-simulation failure handling (the reference aborts the whole run on any exception; the
+engine flags the simulation in `status` and keeps the batch going), empty batches, bad arguments."""
+import numpy as np
+import pytest
+
+import mcos_b200 as mb
+from mcos_b200 import _lib
+from mcos_b200.engine import Engine
+from mcos_b200.synthetic import block_diagonal_truth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def test_nan_in_one_simulation_does_not_poison_or_hang_the_batch():
+    n, t = 40, 100
+    mu, cov = block_diagonal_truth(n, n_blocks=4)
+    rng = np.random.RandomState(0)
+    covs = np.stack([np.cov(rng.multivariate_normal(mu, cov, size=t), rowvar=False) for _ in range(4)])
+    mus = np.tile(mu, (4, 1))
+    bad = covs.copy()
+    bad[2, 3, 5] = bad[2, 5, 3] = np.nan
+    eng = Engine(n, t)
+    good_d, _ = eng.denoise(covs, t)
+    d, info = eng.denoise(bad, t)
+    assert info["status"][2] != 0 and (info["status"][[0, 1, 3]] == 0).all()
+    assert np.array_equal(d[[0, 1, 3]], good_d[[0, 1, 3]])
+    for fn in (lambda c: eng.hrp(c), lambda c: eng.markowitz(mus, c), lambda c: eng.nco(mus, c, 4, 1),
+               lambda c: eng.risk_parity(c)):
+        w_good, _ = fn(covs)
+        w_bad, _ = fn(bad)                                # must return (no hang); the clean simulations are untouched
+        assert np.array_equal(w_bad[[0, 1, 3]], w_good[[0, 1, 3]])
+
+
+def test_singular_sample_covariance():
+    """T < N: the sample covariance is singular. HRP and Ledoit-Wolf + DeNoiser are well defined; Markowitz on the raw
+    singular matrix either solves (the free set stays non-singular) or flags NOT_PD -- it must not hang or return junk."""
+    n, t = 30, 12
+    mu, cov = block_diagonal_truth(n, n_blocks=3)
+    sim = mb.MuCovObservationSimulator(mu, cov, t, seed=5)
+    mu_hat, cov_hat = sim.simulate_batch(6)
+    eng = Engine(n, t)
+    w, info = eng.hrp(cov_hat)
+    assert (info["status"] == 0).all() and np.allclose(w.sum(1), 1.0)
+    wm, minfo = eng.markowitz(mu_hat, cov_hat, clean=False)
+    for i in range(6):
+        if minfo["status"][i] == 0:
+            assert abs(wm[i].sum() - 1) < 1e-9 and (wm[i] >= 0).all()
+        else:
+            assert minfo["status"][i] & (_lib.ST_NOT_PD | _lib.ST_QP_CAP | _lib.ST_NO_EXCESS)
+    lw = mb.MuCovLedoitWolfObservationSimulator(mu, cov, t, seed=5)
+    errs, st = mb.simulate_errors(lw, 6, [mb.MarkowitzOptimizer(), mb.HRPOptimizer()], mb.VarianceErrorEstimator(),
+                                  [mb.DeNoiserCovarianceTransformer()])
+    assert np.isfinite(errs).all()
+
+
+def test_empty_batches_and_bad_arguments():
+    eng = Engine(10, 20)
+    mu, cov = block_diagonal_truth(10, n_blocks=2)
+    eng.set_truth(mu, cov)
+    assert eng.sample(0).shape == (0, 20, 10)
+    w, info = eng.hrp(np.zeros((0, 10, 10)))
+    assert w.shape == (0, 10)
+    plan = mb.build_plan(mb.MuCovObservationSimulator(mu, cov, 20), [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [])
+    err, st = eng.run(plan, 0)
+    assert err.shape == (0, 1)
+    with pytest.raises(_lib.MCOSBError):
+        eng.detone(cov[None], 17)                          # more than 16 components
+    with pytest.raises(_lib.MCOSBError):
+        eng.moments(np.zeros((1, 20, 10)), 7)              # unknown estimator kind
+    fresh = Engine(10, 20)
+    with pytest.raises(_lib.MCOSBError):
+        fresh.sample(1)                                    # truth not set
+    with pytest.raises(_lib.MCOSBError):
+        Engine(0, 5)
+
+
+def test_hrp_sum_check_and_markowitz_no_excess_raise_like_the_reference():
+    mu, cov = block_diagonal_truth(20, n_blocks=2)
+    with pytest.raises(ValueError):
+        mb.MarkowitzOptimizer().allocate(np.full(20, 0.001), cov)   # nothing above the risk-free rate
+    sim = mb.MuCovObservationSimulator(np.full(20, 0.001), cov, 50)
+    with pytest.raises(ValueError):
+        mb.simulate_optimizations(sim, 4, [mb.MarkowitzOptimizer()], mb.VarianceErrorEstimator(), [])
