@@ -33,7 +33,9 @@ enum {
     MCOSB_ERR_ARG = -1,      /* bad argument */
     MCOSB_ERR_CUDA = -2,     /* CUDA runtime error (text in mcosb_last_error) */
     MCOSB_ERR_STATE = -3,    /* e.g. truth not set */
-    MCOSB_ERR_NOT_PD = -4    /* true covariance is not positive definite (Cholesky failed) */
+    MCOSB_ERR_NOT_PD = -4,   /* true covariance is not positive definite (Cholesky failed) */
+    MCOSB_ERR_IDEAL = -5     /* mcosb_run: an optimizer failed on the TRUE (mu, cov) (mcos.py:30 would raise); the
+                                MCOSB_ST_* bits are the last integer of mcosb_last_error */
 };
 
 /* per-simulation status bits */
@@ -85,6 +87,16 @@ int mcosb_moments(mcosb_ctx* ctx, int S, const double* X, int kind, double* mu_h
  * Nullable outputs: eigvals[S][N] (descending), var[S] (fitted MP variance), n_facts[S], status[S]. */
 int mcosb_denoise(mcosb_ctx* ctx, int S, double* cov_inout, int n_obs, double bandwidth, double* eigvals, double* var,
                   int* n_facts, int* status);
+
+/* Selects the tridiagonalisation behind np.linalg.eigh (covariance_transformer.py:105) in mcosb_denoise / mcosb_detone /
+ * mcosb_run: 0 = automatic (two-stage for 96 <= n_assets <= 712), 1 = one-stage blocked Householder, 2 = two-stage
+ * (dense -> band on the FP64 tensor cores, band -> tridiagonal by bulge chasing in shared memory). */
+int mcosb_set_eig_method(mcosb_ctx* ctx, int method);
+
+/* Diagnostic: tridiagonal form (d[S][N], e[S][N] with e[i] = T[i+1][i], e[N-1] = 0) of symmetric matrices sym[S][N][N]
+ * by the selected method -- the first half of np.linalg.eigh (covariance_transformer.py:105).  a_work[S][N][N]
+ * (nullable) receives the work matrix holding the Householder reflectors. */
+int mcosb_tridiagonalize(mcosb_ctx* ctx, int S, const double* sym, double* d, double* e, double* a_work);
 
 /* DetoneCovarianceTransformer.transform (covariance_transformer.py:222-250), in place on cov[S][N][N]: removes the
  * n_remove (0..16) largest eigen-components of the correlation matrix, renormalises it to unit diagonal and rescales by

@@ -16,6 +16,7 @@ MOMENTS_MUCOV, MOMENTS_LEDOIT_WOLF, MOMENTS_JACKKNIFE = 0, 1, 2
 ERR_EXPECTED_OUTCOME, ERR_VARIANCE, ERR_SHARPE = 0, 1, 2
 OPT_MARKOWITZ, OPT_HRP, OPT_NCO, OPT_RISK_PARITY = 0, 1, 2, 3
 
+ERR_IDEAL = -5
 ST_NOT_PD, ST_NO_EXCESS, ST_QP_CAP, ST_MPFIT_FAIL, ST_EIGVEC, ST_HRP_SUM, ST_NONFINITE = 1, 2, 4, 8, 16, 32, 64
 
 
@@ -41,6 +42,8 @@ SIGNATURES = {
     "mcosb_sample": (c_int, [c_void_p, c_uint64, c_int, c_void_p]),
     "mcosb_moments": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mcosb_denoise": (c_int, [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcosb_set_eig_method": (c_int, [c_void_p, c_int]),
+    "mcosb_tridiagonalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_detone": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "mcosb_markowitz": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "mcosb_hrp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

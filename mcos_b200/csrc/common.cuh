@@ -19,7 +19,7 @@ enum ScratchSlot {
     SL_MK_L, SL_MK_W, SL_MK_ITERS,
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
     SL_NCO_W, SL_NCO_LABELS, SL_NCO_WORK, SL_NCO_E,
-    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W,
+    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2,
     SL_COUNT
 };
 
@@ -53,6 +53,9 @@ enum KernelId {
     MK_RECONSTRUCT,
     MK_DETONE,
     MK_RISK_PARITY,
+    MK_SY2SB,
+    MK_SB2ST,
+    MK_Q2BACK,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -84,7 +87,10 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "backtransform",
     "reconstruct",
     "detone",
-    "risk_parity"
+    "risk_parity",
+    "sy2sb",
+    "sb2st",
+    "q2back"
 };
 
 struct mcosb_ctx {
@@ -104,6 +110,7 @@ struct mcosb_ctx {
     double stage_ms[MCOSB_N_STAGES] = {};
     int smem_optin = 0;
     int num_sms = MCOSB_SMS;
+    int eig_method = 0;  // 0 auto, 1 one-stage Householder (tridiag / tridiag2), 2 two-stage (sy2sb + sb2st)
     // per-kernel timing (mcosb_set_profiling): one event after every launch; a kernel's time is the gap to the
     // previous event on the stream
     bool profile = false;
@@ -284,8 +291,10 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX);
 int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink);
 int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
                       int* dnf, int* dstatus);
+// *q2 receives the stage-2 reflectors when the two-stage tridiagonalisation was used (then A holds the panel reflectors
+// of sy2sb_kernel, offset 8), nullptr for the one-stage kernels (offset 1)
 int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, double* sigma, double* d, double* e,
-                          double* tau, double* lam);
+                          double* tau, double* lam, const double** q2);
 int mcosb_dev_detone(mcosb_ctx* ctx, int S, double* dcov, int n_remove, int* dstatus);
 int mcosb_dev_risk_parity(mcosb_ctx* ctx, int S, const double* dcov, const double* dbudget, double* dw, int* diters,
                           int* dstatus);

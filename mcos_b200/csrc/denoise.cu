@@ -11,10 +11,12 @@
 // (4 MB) resident; Householder + bisection costs 4/3 N^3 (1.7e8) and only the n_facts (~10) eigenvectors the
 // reconstruction needs are ever formed:  V L' V' = lbar I + V_s (L_s - lbar I) V_s'  because V V' = I.
 #include "common.cuh"
+#include "sbr.cuh"
 
 int mcosb_launch_tridiag2(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau);
 int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d, const double* e, const double* tau,
-                         const double* lam, const int* nf, const double* sigma, double* cov, int* status);
+                         const double* lam, const int* nf, const double* sigma, double* cov, int* status,
+                         const double* Q2);
 
 // ---------------------------------------------------------------------------------------------------------------
 // D1: correlation matrix.  grid = (ceil(N/8), S), 256 threads, one warp per row.
@@ -623,8 +625,9 @@ __global__ void __launch_bounds__(VC_THREADS) eigvec_kernel(const double* __rest
                                                             double* __restrict__ workall,  // [S][5][N][VC_VCH]
                                                             unsigned char* __restrict__ pivall,  // [S][N][VC_VCH]
                                                             double* __restrict__ covall, int* __restrict__ status,
-                                                            int skip_upto) {
+                                                            int skip_upto, const double* __restrict__ Q2all) {
     if (nfall[blockIdx.x] <= skip_upto) return;  // handled by the wide path (eigvec3.cu)
+    const int off = Q2all ? SBR_B : 1;           // two-stage reflectors: Q2 (sb2st.cu) first, then the panels of sy2sb.cu
     extern __shared__ double sm[];
     double* sd = sm;                  // [N]
     double* se = sd + N;              // [N]
@@ -741,18 +744,34 @@ __global__ void __launch_bounds__(VC_THREADS) eigvec_kernel(const double* __rest
         // ---- back-transformation, one warp per vector ------------------------------------------------------------------
         if (wid < nv) {
             double* yv = ys + (size_t)wid * N;
-            for (int k = N - 3; k >= 0; --k) {
+            if (Q2all) {
+                // y <- Q2 y: the reflectors of a sweep act on disjoint windows of 8 rows, one lane each
+                const double* Q2 = Q2all + (size_t)s * N * N;
+                for (int sw = N - 3; sw >= 0; --sw) {
+                    const double* q = Q2 + (size_t)sw * N;
+                    for (int lo = sw + 1 + 8 * lane; N - lo >= 2; lo += 8 * 32) {
+                        const double tq = q[lo - sw - 1];
+                        double dot = yv[lo];
+                        for (int m = 1; m < 8 && lo + m < N; ++m) dot = fma(q[lo - sw - 1 + m], yv[lo + m], dot);
+                        dot *= tq;
+                        yv[lo] -= dot;
+                        for (int m = 1; m < 8 && lo + m < N; ++m) yv[lo + m] = fma(-dot, q[lo - sw - 1 + m], yv[lo + m]);
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int k = N - 2 - off; k >= 0; --k) {
                 const double tk = tau[k];
                 if (tk == 0.0) continue;
-                const double* u = A + (size_t)k * N;  // u[k+1] = 1 implicit, u[j] = A[k][j] for j >= k+2
+                const double* u = A + (size_t)k * N;  // u[k+off] = 1 implicit, u[j] = A[k][j] for j > k+off
                 double dot = 0.0;
-                for (int jj = k + 1 + lane; jj < N; jj += 32) {
-                    double uj = (jj == k + 1) ? 1.0 : u[jj];
+                for (int jj = k + off + lane; jj < N; jj += 32) {
+                    double uj = (jj == k + off) ? 1.0 : u[jj];
                     dot = fma(uj, yv[jj], dot);
                 }
                 dot = warp_sum(dot) * tk;
-                for (int jj = k + 1 + lane; jj < N; jj += 32) {
-                    double uj = (jj == k + 1) ? 1.0 : u[jj];
+                for (int jj = k + off + lane; jj < N; jj += 32) {
+                    double uj = (jj == k + off) ? 1.0 : u[jj];
                     yv[jj] = fma(-dot, uj, yv[jj]);
                 }
                 __syncwarp();
@@ -780,15 +799,26 @@ __global__ void __launch_bounds__(VC_THREADS) eigvec_kernel(const double* __rest
     if (status && __syncthreads_or(bad_vec) && tid == 0) atomicOr(&status[s], MCOSB_ST_EIGVEC);
 }
 
-// corr = cov_to_corr(cov) -> Householder tridiagonalisation (reflectors left in A) -> all eigenvalues, descending.
-// Shared by the DeNoiser and the Detone transformer.
-int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, double* sigma, double* d, double* e,
-                          double* tau, double* lam) {
+// Symmetric A[S][N][N] (lower triangle read) -> tridiagonal (d, e), reflectors left in A / tau (/ *q2).
+int mcosb_dev_tridiagonalize(mcosb_ctx* ctx, int S, double* A, double* d, double* e, double* tau, const double** q2) {
     const int N = ctx->N;
     const size_t n = (size_t)N;
-    corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
-    MCOSB_LAUNCHED(ctx, MK_CORR);
-
+    *q2 = nullptr;
+    const bool sbr = mcosb_sbr_supported(ctx) && (ctx->eig_method == 2 || (ctx->eig_method == 0 && N >= SBR_MIN_N));
+    if (ctx->eig_method == 2 && !sbr)
+        return mcosb_fail(ctx, MCOSB_ERR_ARG, "two-stage tridiagonalisation needs 10 <= n_assets <= 712");
+    if (sbr) {
+        // two-stage: dense -> band (sy2sb.cu, DMMA) -> tridiagonal (sb2st.cu, bulge chasing in shared memory)
+        double* Q2;
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_Q2, (size_t)S * n * n, &Q2));
+        int r1 = mcosb_launch_sy2sb(ctx, S, A, tau);
+        if (r1 < 0) return r1;
+        int r2 = r1 == 1 ? mcosb_launch_sb2st(ctx, S, A, d, e, Q2) : 0;
+        if (r2 < 0) return r2;
+        if (r1 != 1 || r2 != 1) return mcosb_fail(ctx, MCOSB_ERR_STATE, "two-stage tridiagonalisation failed to launch");
+        *q2 = Q2;
+        return MCOSB_OK;
+    }
     int r2 = mcosb_launch_tridiag2(ctx, S, A, d, e, tau);  // blocked, lower triangle only (tridiag2.cu)
     if (r2 < 0) return r2;
     if (r2 == 1) {
@@ -799,11 +829,53 @@ int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, 
         tridiag_kernel<<<S, TD_THREADS, smem_td, ctx->stream>>>(A, N, d, e, tau);
         MCOSB_LAUNCHED(ctx, MK_TRIDIAG);
     }
+    return MCOSB_OK;
+}
 
+// corr = cov_to_corr(cov) -> tridiagonalisation (reflectors left in A) -> all eigenvalues, descending.
+// Shared by the DeNoiser and the Detone transformer.
+int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, double* sigma, double* d, double* e,
+                          double* tau, double* lam, const double** q2) {
+    const int N = ctx->N;
+    const size_t n = (size_t)N;
+    corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
+    MCOSB_LAUNCHED(ctx, MK_CORR);
+    MCOSB_TRY(mcosb_dev_tridiagonalize(ctx, S, A, d, e, tau, q2));
     size_t smem_ev = 2 * n * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ev));
     eigvals_kernel<<<S, EV_THREADS, smem_ev, ctx->stream>>>(d, e, N, lam);
     MCOSB_LAUNCHED(ctx, MK_EIGVALS);
+    return MCOSB_OK;
+}
+
+// Diagnostic entry point: the tridiagonal form of symmetric matrices (first half of np.linalg.eigh,
+// covariance_transformer.py:105), by the selected method.  The work copy of A (reflectors / band) comes back in A_work.
+extern "C" int mcosb_tridiagonalize(mcosb_ctx* ctx, int S, const double* sym, double* d_out, double* e_out,
+                                    double* a_work) {
+    MCOSB_CHECK_CTX(ctx);
+    if (S < 0 || !sym || !d_out || !e_out) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_tridiagonalize");
+    if (S == 0) return MCOSB_OK;
+    const size_t n = ctx->N;
+    Staging st(ctx);
+    const double* dsym;
+    double *dd, *de, *dwork, *A, *tau;
+    MCOSB_TRY(st.in(sym, (size_t)S * n * n, SL_STAGE_IN0, &dsym));
+    MCOSB_TRY(st.out(d_out, (size_t)S * n, SL_STAGE_OUT0, &dd));
+    MCOSB_TRY(st.out(e_out, (size_t)S * n, SL_STAGE_OUT1, &de));
+    MCOSB_TRY(st.out(a_work, (size_t)S * n * n, SL_STAGE_OUT2, &dwork));
+    if (dwork) A = dwork;
+    else MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_A, (size_t)S * n * n, &A));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_TAU, (size_t)S * n, &tau));
+    MCOSB_CUDA(ctx, cudaMemcpyAsync(A, dsym, (size_t)S * n * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    const double* q2 = nullptr;
+    MCOSB_TRY(mcosb_dev_tridiagonalize(ctx, S, A, dd, de, tau, &q2));
+    return st.finish();
+}
+
+extern "C" int mcosb_set_eig_method(mcosb_ctx* ctx, int method) {
+    MCOSB_CHECK_CTX(ctx);
+    if (method < 0 || method > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "eig method must be 0 (auto), 1 or 2");
+    ctx->eig_method = method;
     return MCOSB_OK;
 }
 
@@ -824,7 +896,8 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     if (!lam) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_LAM, (size_t)S * n, &lam));
     nf = dnf;
     if (!nf) MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_NF, (size_t)S, &nf));
-    MCOSB_TRY(mcosb_dev_eig_prepare(ctx, S, dcov, A, sigma, d, e, tau, lam));
+    const double* Q2 = nullptr;
+    MCOSB_TRY(mcosb_dev_eig_prepare(ctx, S, dcov, A, sigma, d, e, tau, lam, &Q2));
 
     const double q = (double)n_obs / (double)N;
     size_t smem_mp = n * sizeof(double);
@@ -833,7 +906,7 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     MCOSB_LAUNCHED(ctx, MK_MPFIT);
 
     // wide path (eigvec3.cu) for simulations with at most 16 signal eigenvalues; eigvec_kernel takes the others
-    int rv = mcosb_launch_eigvec3(ctx, S, A, d, e, tau, lam, nf, sigma, dcov, dstatus);
+    int rv = mcosb_launch_eigvec3(ctx, S, A, d, e, tau, lam, nf, sigma, dcov, dstatus, Q2);
     if (rv < 0) return rv;
     {
         double* work2;
@@ -844,7 +917,7 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
         if (smem_vc > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for eigvec_kernel");
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vc));
         eigvec_kernel<<<S, VC_THREADS, smem_vc, ctx->stream>>>(A, N, d, e, tau, lam, nf, sigma, work2, piv2, dcov, dstatus,
-                                                              rv == 1 ? 16 : -1);
+                                                              rv == 1 ? 16 : -1, Q2);
         MCOSB_LAUNCHED(ctx, MK_EIGVEC);
     }
     return MCOSB_OK;

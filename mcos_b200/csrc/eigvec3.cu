@@ -12,6 +12,7 @@
 //   reconstruct_kernel    elementwise: cov_ij = clip((lbar d_ij + sum_s (lam_s - lbar) v_si v_sj) / sqrt(r_i r_j)) s_i s_j.
 // Simulations with more than EV3_VMAX signal eigenvalues are left to eigvec_kernel (it skips the others).
 #include "common.cuh"
+#include "sbr.cuh"
 
 #define EV3_VMAX 16
 
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
                                                             const double* __restrict__ tauall,
                                                             const int* __restrict__ nfall, int N, int S,
                                                             const double* __restrict__ W, double* __restrict__ V,
-                                                            int* __restrict__ status) {
+                                                            int* __restrict__ status, int off) {
     const size_t G = (size_t)S * EV3_VMAX;
     const size_t g = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -143,8 +144,9 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
     }
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) yr[m] *= sc;
-    // y <- H_0 ... H_{N-3} y ; reflector k: u[k+1] = 1, u[j] = A[k][j] for j >= k+2
-    for (int k = N - 3; k >= 0; --k) {
+    // y <- H_0 ... H_{N-2-off} y ; reflector k: u[k+off] = 1, u[j] = A[k][j] for j > k+off
+    // (off = 1: one-stage tridiagonalisation; off = 8: panel reflectors of sy2sb_kernel)
+    for (int k = N - 2 - off; k >= 0; --k) {
         const double tk = tau[k];
         if (tk == 0.0) continue;
         const double* u = A + (size_t)k * N;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
             const int j = lane + 32 * m;
-            ur[m] = (j > k + 1 && j < N) ? u[j] : ((j == k + 1) ? 1.0 : 0.0);
+            ur[m] = (j > k + off && j < N) ? u[j] : ((j == k + off) ? 1.0 : 0.0);
             dot = fma(ur[m], yr[m], dot);
         }
         dot = warp_sum(dot) * tk;
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(const double* __restri
 // Launches the three kernels. Returns 1 if used (simulations with nf > EV3_VMAX still need eigvec_kernel), 0 if N is
 // out of range for the register back-transformation, < 0 on error.
 int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d, const double* e, const double* tau,
-                         const double* lam, const int* nf, const double* sigma, double* cov, int* status) {
+                         const double* lam, const int* nf, const double* sigma, double* cov, int* status,
+                         const double* Q2) {
     const int N = ctx->N;
     const size_t n = (size_t)N;
     if (N > 1024) return 0;
@@ -227,11 +230,13 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_VAR, n * G, &V));
     inviter_kernel<<<(unsigned)((G + 63) / 64), 64, 0, ctx->stream>>>(d, e, lam, nf, N, S, W, piv);
     MCOSB_LAUNCHED(ctx, MK_INVITER);
+    const int off = Q2 ? SBR_B : 1;
+    if (Q2) MCOSB_TRY(mcosb_launch_q2back(ctx, S, Q2, nf, W + 4 * n * G) == 1 ? MCOSB_OK : MCOSB_ERR_STATE);
     const unsigned bt_grid = (unsigned)((G + 7) / 8);
-    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status);
-    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status);
-    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status);
-    else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status);
+    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     const size_t smem = (n + EV3_VMAX) * sizeof(double);
     reconstruct_kernel<<<dim3((N + 7) / 8, S), 256, smem, ctx->stream>>>(V, lam, nf, sigma, N, cov);
@@ -307,16 +312,19 @@ int mcosb_dev_detone(mcosb_ctx* ctx, int S, double* dcov, int n_remove, int* dst
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_WORK, 5 * n * G, &W));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_VEC, n * G, &piv));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_VAR, n * G, &V));
-    MCOSB_TRY(mcosb_dev_eig_prepare(ctx, S, dcov, A, sigma, d, e, tau, lam));
+    const double* Q2 = nullptr;
+    MCOSB_TRY(mcosb_dev_eig_prepare(ctx, S, dcov, A, sigma, d, e, tau, lam, &Q2));
+    const int off = Q2 ? SBR_B : 1;
     fill_int_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(nf, (size_t)S, n_remove);
     MCOSB_LAUNCHED(ctx, MK_FILL);
     inviter_kernel<<<(unsigned)((G + 63) / 64), 64, 0, ctx->stream>>>(d, e, lam, nf, N, S, W, piv);
     MCOSB_LAUNCHED(ctx, MK_INVITER);
+    if (Q2) MCOSB_TRY(mcosb_launch_q2back(ctx, S, Q2, nf, W + 4 * n * G) == 1 ? MCOSB_OK : MCOSB_ERR_STATE);
     const unsigned bt_grid = (unsigned)((G + 7) / 8);
-    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
-    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
-    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
-    else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus);
+    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     detone_kernel<<<dim3((N + 7) / 8, S), 256, n * sizeof(double), ctx->stream>>>(V, lam, n_remove, sigma, N, dcov);
     MCOSB_LAUNCHED(ctx, MK_DETONE);

@@ -157,7 +157,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     if (ideal_status) {
         char buf[128];
         snprintf(buf, sizeof buf, "ideal allocation on the true (mu, cov) failed with status bits %d", ideal_status);
-        return mcosb_fail(ctx, MCOSB_ERR_STATE, buf);
+        return mcosb_fail(ctx, MCOSB_ERR_IDEAL, buf);
     }
     return MCOSB_OK;
 }

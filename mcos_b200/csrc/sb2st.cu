@@ -1,0 +1,237 @@
+// Stage 2 of the two-stage tridiagonalisation: symmetric band (half bandwidth 8, left in the lower band of A by
+// sy2sb_kernel) -> tridiagonal, by bulge chasing, entirely in shared memory; and the matching back-transformation.
+//
+// Sweep s annihilates column s below the sub-diagonal with a length-8 Householder reflector on rows s+1 .. s+8; applied
+// two-sidedly it fills the 8 x 8 block below the band (the bulge), whose first column is annihilated by the next
+// reflector on rows s+9 .. s+16, and so on down the band (step k works on rows lo .. lo+7, lo = s + 1 + 8 k).  Only the
+// first column of each bulge is removed; the rest stays until the next sweep reaches it, so the band is held with 16
+// diagonals: Bs[j][d] = B[j + d][j], 128 bytes per column, 64 KB per 500 x 500 matrix -> three matrices per SM.
+//
+// One warp executes a step.  Three groups of 8 lanes hold 8 values each, addressed lo * 16 + off[m] with per-lane
+// offsets that never change:
+//   lanes  0- 7  column c of C_k     = B[lo.., lo-8+c]   left application   z -= tau (v . z) v
+//   lanes  8-15  row r of D_k        = B[lo+r, lo..]     two-sided          z -= v_r w + w_r v,  w = p - (tau/2)(v . p) v
+//   lanes 16-23  row r of C_{k+1}    = B[lo+8+r, lo..]   right application  z -= tau (z . v) v
+// so every reduction is a private dot product; the only cross-lane traffic is the broadcast of x (lane 0's values) and
+// of w.  Rows and columns beyond N are zero padding and stay zero, which handles the short windows at the end of the band.
+//
+// W warps work on one matrix as a software pipeline: warp u owns sweeps s = u (mod W) and may run step k of sweep s once
+// sweep s - 1 has completed step k + 2 (the two then touch disjoint elements); progress is published through shared
+// memory.  The reflectors go to Q2[s][lo - s - 1 + m] (tau in the slot of the implicit 1) for q2back_kernel.
+#include "common.cuh"
+#include "sbr.cuh"
+
+template <int W>
+__global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict__ Aall, int N, double* __restrict__ dall,
+                                                       double* __restrict__ eall, double* __restrict__ Q2all) {
+    extern __shared__ double Bs[];                 // [(N + 16) * 16]
+    __shared__ volatile int prog[W];
+    const int sim = blockIdx.x;
+    const double* A = Aall + (size_t)sim * N * N;
+    double* Q2 = Q2all + (size_t)sim * N * N;
+    const int tid = threadIdx.x, lane = tid & 31, u = tid >> 5;
+    constexpr int NT = W * 32;
+
+    for (int i = tid; i < (N + 16) * 16; i += NT) Bs[i] = 0.0;
+    if (tid < W) prog[tid] = -1;
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) {
+        const double* row = A + (size_t)i * N;
+        for (int d = 0; d <= SBR_B && d <= i; ++d) Bs[(i - d) * 16 + d] = row[i - d];
+    }
+    __syncthreads();
+
+    const int grp = lane >> 3, l = lane & 7;
+    int off[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (grp == 0) off[m] = (l - 8) * 16 + 8 - l + m;
+        else if (grp == 1) off[m] = (l < m ? l : m) * 16 + (l < m ? m - l : l - m);
+        else off[m] = m * 16 + 8 + l - m;
+    }
+    const bool g0 = grp == 0, g1 = grp == 1;
+    const int pu = (u + W - 1) % W;
+    int seen = -1;   // last progress value read from the predecessor
+
+    for (int s = u; s + 2 < N; s += W) {
+        for (int k = 0;; ++k) {
+            const int lo = s + 1 + 8 * k;
+            if (N - lo < 2) break;
+            if (s > 0) {
+                int need_done = k + 3;
+                if (need_done > 255) need_done = 255;
+                const int need = (s - 1) * 256 + need_done;
+                if (seen < need) {
+                    if (lane == 0) {
+                        int cur = prog[pu];
+                        // the predecessor publishes 255 when its sweep is complete
+                        while (cur < need && !(cur >= (s - 1) * 256 + 255)) {
+                            __nanosleep(40);
+                            cur = prog[pu];
+                        }
+                        seen = cur;
+                    }
+                    seen = __shfl_sync(0xffffffffu, seen, 0);
+                    __threadfence_block();
+                }
+            }
+            const int base = lo * 16;
+            const bool k0 = (k == 0) && g0;
+            const bool dead = (k0 && l != 0) || grp == 3;
+            double z[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int o = k0 ? (m - 15) : off[m];
+                z[m] = Bs[base + o];
+                if (dead) z[m] = 0.0;
+            }
+            double x[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) x[m] = __shfl_sync(0xffffffffu, z[m], 0);
+            double ss = 0.0;
+#pragma unroll
+            for (int m = 1; m < 8; ++m) ss = fma(x[m], x[m], ss);
+            const double alpha = x[0];
+            double tau = 0.0, scale = 0.0, beta = alpha;
+            if (ss > 0.0) {
+                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            double v[8];
+            v[0] = 1.0;
+#pragma unroll
+            for (int m = 1; m < 8; ++m) v[m] = x[m] * scale;
+            double dot = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) dot = fma(v[m], z[m], dot);
+            const double p = tau * dot;
+            double vr = v[0];
+#pragma unroll
+            for (int m = 1; m < 8; ++m) vr = (l == m) ? v[m] : vr;
+            double kp = vr * p;
+            kp += __shfl_xor_sync(0xffffffffu, kp, 1);
+            kp += __shfl_xor_sync(0xffffffffu, kp, 2);
+            kp += __shfl_xor_sync(0xffffffffu, kp, 4);
+            const double wr = fma(-0.5 * tau * kp, vr, p);
+            const double a1 = g1 ? vr : p;
+            const double a2 = g1 ? wr : 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const double wm = __shfl_sync(0xffffffffu, wr, 8 + m);
+                const double b1 = g1 ? wm : v[m];
+                z[m] = fma(-a2, v[m], fma(-a1, b1, z[m]));
+            }
+            if (g0 && l == 0) {
+                z[0] = beta;
+#pragma unroll
+                for (int m = 1; m < 8; ++m) z[m] = 0.0;
+            }
+            if (!dead) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const int o = k0 ? (m - 15) : off[m];
+                    if (!g1 || m <= l) Bs[base + o] = z[m];
+                }
+            }
+            if (lane < 8 && lo + lane < N) {
+                double q = tau;
+#pragma unroll
+                for (int m = 1; m < 8; ++m) q = (lane == m) ? v[m] : q;
+                Q2[(size_t)s * N + (lo - s - 1) + lane] = q;
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) prog[u] = s * 256 + k + 1;
+        }
+        __syncwarp();
+        if (lane == 0) prog[u] = s * 256 + 255;
+    }
+    __syncthreads();
+    double* d = dall + (size_t)sim * N;
+    double* e = eall + (size_t)sim * N;
+    for (int i = tid; i < N; i += NT) {
+        d[i] = Bs[i * 16];
+        e[i] = (i + 1 < N) ? Bs[i * 16 + 1] : 0.0;
+    }
+}
+
+int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double* e, double* Q2) {
+    const int N = ctx->N;
+    const size_t smem = (size_t)(N + 16) * 16 * sizeof(double);
+    if (smem + 1024 > (size_t)ctx->smem_optin || N > 768) return 0;
+    constexpr int W = 4;
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sb2st_kernel<W><<<S, W * 32, smem, ctx->stream>>>(A, N, d, e, Q2);
+    MCOSB_LAUNCHED(ctx, MK_SB2ST);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// y <- Q2 y for the inverse-iteration vectors of one simulation (layout of inviter_kernel: y[i * G + g]).  The
+// reflectors of one sweep act on disjoint row windows, so a sweep is one parallel step over (reflector, vector) pairs;
+// sweeps run last to first.  The vectors sit in shared memory as Y[row][vector].
+// ---------------------------------------------------------------------------------------------------------------
+#define Q2B_NT 256
+#define Q2B_V 16   // = EV3_VMAX
+
+__global__ void __launch_bounds__(Q2B_NT) q2back_kernel(const double* __restrict__ Q2all, const int* __restrict__ nfall,
+                                                        int N, int S, double* __restrict__ Wy) {
+    extern __shared__ double Y[];                  // [(N + 8)][16]
+    const int sim = blockIdx.x, tid = threadIdx.x;
+    const int nf = nfall[sim];
+    if (nf > Q2B_V || nf <= 0) return;
+    const size_t G = (size_t)S * Q2B_V;
+    double* y = Wy + sim * (size_t)Q2B_V;          // element (i, vec) at y[i * G + vec]
+    const double* Q2 = Q2all + (size_t)sim * N * N;
+    for (int idx = tid; idx < (N + 8) * Q2B_V; idx += Q2B_NT) {
+        const int i = idx >> 4, vec = idx & 15;
+        Y[idx] = (i < N && vec < nf) ? y[(size_t)i * G + vec] : 0.0;
+    }
+    __syncthreads();
+    for (int s = N - 3; s >= 0; --s) {
+        const int nk = (N - 3 - s) / 8 + 1;
+        const double* q = Q2 + (size_t)s * N;
+        for (int item = tid; item < nk * Q2B_V; item += Q2B_NT) {
+            const int k = item >> 4, vec = item & 15;
+            if (vec < nf) {
+                const int lo = s + 1 + 8 * k;
+                const double tau = q[8 * k];
+                double v[8], yy[8];
+                v[0] = 1.0;
+#pragma unroll
+                for (int m = 1; m < 8; ++m) v[m] = (lo + m < N) ? q[8 * k + m] : 0.0;
+                double dot = 0.0;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    yy[m] = Y[(lo + m) * Q2B_V + vec];
+                    dot = fma(v[m], yy[m], dot);
+                }
+                dot *= tau;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) Y[(lo + m) * Q2B_V + vec] = fma(-dot, v[m], yy[m]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < N * Q2B_V; idx += Q2B_NT) {
+        const int i = idx >> 4, vec = idx & 15;
+        if (vec < nf) y[(size_t)i * G + vec] = Y[idx];
+    }
+}
+
+int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, double* Wy) {
+    const int N = ctx->N;
+    const size_t smem = (size_t)(N + 8) * Q2B_V * sizeof(double);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(q2back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    q2back_kernel<<<S, Q2B_NT, smem, ctx->stream>>>(Q2, nf, N, S, Wy);
+    MCOSB_LAUNCHED(ctx, MK_Q2BACK);
+    return 1;
+}
+
+bool mcosb_sbr_supported(mcosb_ctx* ctx) {
+    const int N = ctx->N;
+    extern size_t sbr_stage1_smem(int N);
+    return N >= SBR_B + 2 && N <= 768 && sbr_stage1_smem(N) <= (size_t)ctx->smem_optin &&
+           (size_t)(N + 16) * 16 * sizeof(double) + 1024 <= (size_t)ctx->smem_optin;
+}

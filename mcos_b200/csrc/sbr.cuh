@@ -1,0 +1,15 @@
+// Two-stage tridiagonalisation (successive band reduction): shared constants and launchers.
+//   stage 1  sy2sb.cu   dense symmetric -> band of half bandwidth SBR_B (blocked Householder, DMMA)
+//   stage 2  sb2st.cu   band -> tridiagonal (bulge chasing in shared memory), reflectors kept for the eigenvectors
+//   back     sbback.cu  x = Q1 Q2 y for the signal eigenvectors
+#pragma once
+#include "common.cuh"
+
+#define SBR_B 8
+#define SBR_MIN_N 96   // below this the one-stage kernels are used (mcosb_dev_eig_prepare)
+
+// Each returns 1 if launched, 0 if the problem size is outside its range (nothing launched), < 0 on error.
+int mcosb_launch_sy2sb(mcosb_ctx* ctx, int S, double* A, double* tau);
+int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double* e, double* Q2);
+int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, double* Wy);
+bool mcosb_sbr_supported(mcosb_ctx* ctx);

@@ -146,6 +146,21 @@ class Engine:
         self._check(self.lib.mcosb_denoise(self.h, s, pc, t, float(bandwidth), pe, pv, pn, ps))
         return kc, {"eigvals": eig, "var": var, "n_facts": nf, "status": st}
 
+    def set_eig_method(self, method: int):
+        """0 = automatic, 1 = one-stage Householder tridiagonalisation, 2 = two-stage (band reduction + bulge chasing)."""
+        self._check(self.lib.mcosb_set_eig_method(self.h, int(method)))
+
+    def tridiagonalize(self, sym, want_work=False):
+        """(d, e[, work]) of the symmetric matrices sym[S][N][N]: the first half of np.linalg.eigh on the GPU."""
+        s = sym.shape[0]
+        tt = _is_torch(sym)
+        ks, ps = self._in(sym, (s, self.N, self.N))
+        d, pd_ = self._out(tt, (s, self.N))
+        e, pe = self._out(tt, (s, self.N))
+        wk, pw = self._out(tt, (s, self.N, self.N)) if want_work else (None, None)
+        self._check(self.lib.mcosb_tridiagonalize(self.h, s, ps, pd_, pe, pw))
+        return (d, e, wk) if want_work else (d, e)
+
     def detone(self, cov, n_remove):
         s = cov.shape[0]
         tt = _is_torch(cov)
@@ -214,7 +229,14 @@ class Engine:
     def run(self, plan: Plan, n_sims, sim_id0=0, out_torch=False):
         err, pe = self._out(out_torch, (n_sims, plan.n_optimizers))
         st, ps = self._out(out_torch, (n_sims,), np.int32)
-        self._check(self.lib.mcosb_run(self.h, ctypes.byref(plan), ctypes.c_uint64(sim_id0), n_sims, pe, ps))
+        rc = self.lib.mcosb_run(self.h, ctypes.byref(plan), ctypes.c_uint64(sim_id0), n_sims, pe, ps)
+        if rc == _lib.ERR_IDEAL:  # optimizer.allocate(true mu, true cov) raises in the reference (mcos.py:30)
+            bits = int((self.lib.mcosb_last_error(self.h) or b"0").decode().split()[-1])
+            if bits & _lib.ST_HRP_SUM:
+                raise ValueError("Portfolio allocations don't sum to 1.")
+            if bits & _lib.ST_NO_EXCESS:
+                raise ValueError("no asset has an expected return above the risk-free rate")
+        self._check(rc)
         return err, st
 
 

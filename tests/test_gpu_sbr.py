@@ -1,0 +1,99 @@
+"""GPU: the two-stage tridiagonalisation (sy2sb + sb2st) behind np.linalg.eigh (covariance_transformer.py:105).
+Stage 1 alone (band matrix similar to the input), both stages (tridiagonal similar to the input), and the whole DeNoiser /
+Detone with the one-stage and the two-stage method against each other and the oracle."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import oracle
+from mcos_b200.engine import Engine
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def _corr_batch(n, s, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for k in range(s):
+        t = 2 * n if k % 2 == 0 else max(2, n // 2)        # full rank and rank deficient
+        out.append(np.corrcoef(rng.standard_normal((t, n)) + 0.3 * rng.standard_normal((t, 1)), rowvar=False))
+    return np.stack(out)
+
+
+def _tri_eigs(d, e):
+    n = len(d)
+    t = np.diag(d) + np.diag(e[:n - 1], 1) + np.diag(e[:n - 1], -1)
+    return np.linalg.eigvalsh(t)
+
+
+@pytest.mark.parametrize("n", [10, 11, 16, 17, 18, 25, 33, 64, 65, 96, 100, 129, 200, 257, 333, 500, 512, 513, 700, 712])
+def test_two_stage_tridiagonal_is_similar(n):
+    a = _corr_batch(n, 3, n)
+    eng = Engine(n, 2 * n)
+    eng.set_eig_method(2)
+    d, e, work = eng.tridiagonalize(a, want_work=True)
+    for i in range(a.shape[0]):
+        ref = np.linalg.eigvalsh(a[i])
+        band = np.tril(work[i]) - np.tril(work[i], -9)       # stage 1 leaves the band in the lower 9 diagonals
+        band = band + np.tril(band, -1).T
+        assert_allclose(np.linalg.eigvalsh(band), ref, rtol=0, atol=2e-13 * n)
+        assert_allclose(_tri_eigs(d[i], e[i]), ref, rtol=0, atol=2e-13 * n)
+        assert e[i, n - 1] == 0.0
+
+
+def test_one_stage_still_available():
+    n = 130
+    a = _corr_batch(n, 2, 5)
+    eng = Engine(n, 2 * n)
+    eng.set_eig_method(1)
+    d, e = eng.tridiagonalize(a)
+    for i in range(2):
+        assert_allclose(_tri_eigs(d[i], e[i]), np.linalg.eigvalsh(a[i]), rtol=0, atol=1e-12 * n)
+
+
+@pytest.mark.parametrize("n,t", [(100, 200), (130, 520), (500, 1000), (60, 30), (333, 700)])
+def test_denoise_two_stage_matches_one_stage_and_oracle(n, t):
+    rng = np.random.RandomState(n)
+    a = rng.standard_normal((n, 8)) * (np.arange(8) + 1.0)
+    cov_true = a @ a.T + np.diag(rng.uniform(0.5, 2.0, n))
+    covs = np.stack([np.cov(rng.multivariate_normal(np.zeros(n), cov_true, size=t), rowvar=False) for _ in range(3)])
+    eng = Engine(n, t)
+    eng.set_eig_method(1)
+    out1, info1 = eng.denoise(covs, t)
+    eng.set_eig_method(2)
+    out2, info2 = eng.denoise(covs, t)
+    assert (info1["status"] == 0).all() and (info2["status"] == 0).all()
+    assert np.array_equal(info1["n_facts"], info2["n_facts"])
+    assert_allclose(info2["eigvals"], info1["eigvals"], rtol=0, atol=1e-11 * np.abs(info1["eigvals"]).max())
+    assert_allclose(out2, out1, rtol=1e-8, atol=1e-11 * np.abs(out1).max())
+    d = oracle.denoise_details(covs[0], t)
+    assert int(info2["n_facts"][0]) == int(d["n_facts"])
+    assert_allclose(out2[0], d["cov"], rtol=1e-6, atol=1e-9 * np.abs(d["cov"]).max())
+
+
+def test_many_signal_eigenvalues_take_the_one_cta_path():
+    """More than 16 signal eigenvalues: eigvec_kernel applies Q2 and the panel reflectors itself."""
+    n, t, f = 120, 600, 24
+    rng = np.random.RandomState(3)
+    load = rng.standard_normal((n, f)) * 3.0
+    cov_true = load @ load.T + np.eye(n)
+    covs = np.stack([np.cov(rng.multivariate_normal(np.zeros(n), cov_true, size=t), rowvar=False) for _ in range(2)])
+    eng = Engine(n, t)
+    eng.set_eig_method(2)
+    out, info = eng.denoise(covs, t)
+    assert (info["n_facts"] > 16).all()
+    for i in range(2):
+        d = oracle.denoise_details(covs[i], t)
+        assert int(info["n_facts"][i]) == int(d["n_facts"])
+        assert_allclose(out[i], d["cov"], rtol=1e-6, atol=1e-9 * np.abs(d["cov"]).max())
+
+
+def test_detone_two_stage():
+    n = 150
+    a = _corr_batch(n, 2, 9) * 0.04
+    eng = Engine(n, 2 * n)
+    eng.set_eig_method(1)
+    o1, _ = eng.detone(a, 2)
+    eng.set_eig_method(2)
+    o2, _ = eng.detone(a, 2)
+    assert_allclose(o2, o1, rtol=1e-8, atol=1e-12)
