@@ -806,7 +806,7 @@ int mcosb_dev_tridiagonalize(mcosb_ctx* ctx, int S, double* A, double* d, double
     *q2 = nullptr;
     const bool sbr = mcosb_sbr_supported(ctx) && (ctx->eig_method == 2 || (ctx->eig_method == 0 && N >= SBR_MIN_N));
     if (ctx->eig_method == 2 && !sbr)
-        return mcosb_fail(ctx, MCOSB_ERR_ARG, "two-stage tridiagonalisation needs 10 <= n_assets <= 712");
+        return mcosb_fail(ctx, MCOSB_ERR_ARG, "two-stage tridiagonalisation needs 10 <= n_assets <= 696");
     if (sbr) {
         // two-stage: dense -> band (sy2sb.cu, DMMA) -> tridiagonal (sb2st.cu, bulge chasing in shared memory)
         double* Q2;

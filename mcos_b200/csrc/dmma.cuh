@@ -28,6 +28,13 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                  : "d"(a), "d"(b));
 }
 
+// out of place: (d0, d1) = A B + (c0, c1); the C registers are only read
+__device__ __forceinline__ void dmma_884_oop(double& d0, double& d1, double a, double b, double c0, double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
 // 8-byte asynchronous copy global -> shared; copies nothing and zero-fills when !pred (src must still be a valid address)
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool pred) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -26,7 +26,7 @@ def _tri_eigs(d, e):
     return np.linalg.eigvalsh(t)
 
 
-@pytest.mark.parametrize("n", [10, 11, 16, 17, 18, 25, 33, 64, 65, 96, 100, 129, 200, 257, 333, 500, 512, 513, 700, 712])
+@pytest.mark.parametrize("n", [10, 11, 16, 17, 18, 25, 33, 64, 65, 96, 100, 129, 200, 257, 333, 500, 512, 513, 690, 696])
 def test_two_stage_tridiagonal_is_similar(n):
     a = _corr_batch(n, 3, n)
     eng = Engine(n, 2 * n)
