@@ -60,6 +60,9 @@ def kernel_models(n, t):
         "corr": ("hbm", 16.0 * n * n, "B"),
         "tridiag": ("fp64", 4.0 * n3 / 3, "flop"),                        # Householder tridiagonalisation
         "tridiag2": ("fp64", 4.0 * n3 / 3, "flop"),                       # blocked, lower triangle only
+        "sy2sb": ("tensor", 4.0 * n3 / 3, "flop"),                        # dense -> band (b = 8): rank-16 update + A V on DMMA
+        "sb2st": ("fp64", 6.0 * 8 * n * n, "flop"),                       # bulge chasing, 6 N^2 b flop
+        "q2back": ("hbm", 8.0 * n * n, "B"),                              # stage-2 reflectors read once per simulation
         "eigvals": ("fp64", 2.0 * 2 * 64 * n * n, "flop"),                # 64 bisection steps x N-step Sturm recurrence
         "mpfit": ("fp64", 11 * 1000.0 * n * 25, "flop"),                  # ~11 objective passes x 1000 x N exp (~25 flop)
         "eigvec": ("hbm", 3 * 8.0 * n * n, "B"),                          # reflectors read + cov written and rescaled
@@ -318,16 +321,17 @@ def run_native(args):
     top = max(table, key=lambda k: table[k]["ms"])
     tv = table[top]
     traffic = None   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    traffic_note = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "tridiag2_traffic_r01.json")))
-        if top == "tridiag2" and tr["n_assets"] == N_ASSETS:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "dominant_traffic.json")))[top]
+        if tr["n_assets"] == N_ASSETS:
             traffic = tr["dram_bytes_per_matrix"] * spp
+            traffic_note = tr["note"]
     except Exception:
         pass
     roofline = {"kernel": top + "_kernel", "bound": tv["bound"] if tv["bound"] in ("hbm", "tensor") else "fp64",
                 "achieved": tv["achieved"], "peak": tv["peak"], "unit": tv["unit"], "frac": tv["frac"], "traffic": traffic,
-                "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per matrix (profiles/kernels_final_r01.md) x "
-                                "matrices per launch; algorithmic minimum is 12 N^2 bytes per matrix (3 MB)",
+                "traffic_note": traffic_note,
                 "share_of_step": tv["share"], "ms_per_launch": tv["ms"] / tv["launches"],
                 "peak_source": ("MEASURED_PEAKS.json (%s)" % hbm_src) if tv["bound"] == "hbm"
                 else "profiles/fp64_peaks_r01.json (measured on this pool; MEASURED_PEAKS.json has no FP64 entry)"}

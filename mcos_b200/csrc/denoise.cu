@@ -222,43 +222,56 @@ __global__ void __launch_bounds__(TD_THREADS) tridiag_kernel(double* __restrict_
 
 // ---------------------------------------------------------------------------------------------------------------
 // D3: eigenvalues of the symmetric tridiagonal (d, e) by bisection on the Sturm sequence, one thread per eigenvalue.
-// The Sturm count uses the division-free three-term recurrence p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1} (2 DFMA per
-// step) with exponent rescaling every 8 steps; #sign changes of (p_0..p_N) = #eigenvalues < x.
+// The Sturm count uses the division-free three-term recurrence p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1} (3 FP64
+// instructions per step) with exponent rescaling every 8 steps; #sign changes of (p_0..p_N) = #eigenvalues < x.
 // Output lam[N] sorted DESCENDING (the order _get_PCA produces, covariance_transformer.py:106-107).
 // ---------------------------------------------------------------------------------------------------------------
 #define EV_THREADS 256
 
-__device__ __forceinline__ int sturm_count(const double* __restrict__ sd, const double* __restrict__ se2, int n,
-                                           double x) {
-    double pm = 1.0, pc = sd[0] - x;
-    int cnt = (pc <= 0.0);
-    if (pc == 0.0) pc = -1e-200;  // an exact zero takes the sign opposite to its predecessor (Wilkinson)
-    for (int i = 1; i < n; ++i) {
-        double pn = fma(sd[i] - x, pc, -se2[i - 1] * pm);
-        if (pn == 0.0) pn = -copysign(1e-200, pc);
-        cnt += ((pn < 0.0) != (pc < 0.0));
-        pm = pc;
-        pc = pn;
-        if ((i & 7) == 0) {
-            int ex = ((__double2hiint(pc) >> 20) & 0x7ff) - 1023;
-            int exm = ((__double2hiint(pm) >> 20) & 0x7ff) - 1023;
-            ex = max(ex, exm);
-            if (ex > 300 || ex < -300) {
-                double sc = __hiloint2double((1023 - ex) << 20, 0);
-                pc *= sc;
-                pm *= sc;
-            }
+// sde[i] = (d_i, e_{i-1}^2), e_{-1} = 0.  Only the recurrence itself (DADD, DMUL, DFMA) runs on the FP64 pipe: the sign
+// changes are tracked on the integer pipe from the high words (one funnel shift per step collects the change bits, one
+// popc per 8 steps counts them), and an exact zero takes the sign opposite to its predecessor (Wilkinson) by a select on
+// the sign word instead of a substituted tiny value.
+__device__ __forceinline__ int sturm_count(const double2* __restrict__ sde, int n, double x) {
+    double pm = 0.0, pc = 1.0;
+    int hc = 0, cnt = 0;          // hc: high word carrying the effective sign of p_i
+    unsigned acc = 0;
+#define STURM_STEP(idx)                                                        \
+    {                                                                          \
+        const double2 de = sde[idx];                                           \
+        const double pn = fma(de.x - x, pc, -de.y * pm);                       \
+        const int hn = __double2hiint(pn);                                     \
+        const bool zero = ((hn & 0x7fffffff) | __double2loint(pn)) == 0;       \
+        const int he = zero ? ~hc : hn;                                        \
+        acc = __funnelshift_l((unsigned)(he ^ hc), acc, 1);                    \
+        hc = he;                                                               \
+        pm = pc;                                                               \
+        pc = pn;                                                               \
+    }
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) STURM_STEP(i + k)
+        cnt += __popc(acc);
+        acc = 0;
+        int ex = ((__double2hiint(pc) >> 20) & 0x7ff) - 1023;
+        int exm = ((__double2hiint(pm) >> 20) & 0x7ff) - 1023;
+        ex = max(ex, exm);
+        if (ex > 300 || ex < -300) {
+            const double sc = __hiloint2double((1023 - ex) << 20, 0);
+            pc *= sc;
+            pm *= sc;
         }
     }
-    return cnt;
+    for (; i < n; ++i) STURM_STEP(i)
+#undef STURM_STEP
+    return cnt + __popc(acc);
 }
 
 __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __restrict__ dall,
                                                              const double* __restrict__ eall, int N,
                                                              double* __restrict__ lamall) {
-    extern __shared__ double sm[];
-    double* sd = sm;
-    double* se2 = sm + N;
+    extern __shared__ double2 sde[];   // [N] (d_i, e_{i-1}^2)
     __shared__ double red_lo[EV_THREADS / 32], red_hi[EV_THREADS / 32];
     const int s = blockIdx.x, tid = threadIdx.x;
     const double* d = dall + (size_t)s * N;
@@ -266,8 +279,7 @@ __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __res
     double lo = 1e300, hi = -1e300;
     for (int i = tid; i < N; i += EV_THREADS) {
         double di = d[i], ei = (i < N - 1) ? e[i] : 0.0, em = (i > 0) ? e[i - 1] : 0.0;
-        sd[i] = di;
-        se2[i] = ei * ei;
+        sde[i] = make_double2(di, em * em);
         double r = fabs(ei) + fabs(em);
         lo = fmin(lo, di - r);
         hi = fmax(hi, di + r);
@@ -290,7 +302,7 @@ __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __res
         for (int it = 0; it < 200; ++it) {
             double mid = 0.5 * (a + b);
             if (!(mid > a && mid < b)) break;
-            int c = sturm_count(sd, se2, N, mid);
+            int c = sturm_count(sde, N, mid);
             if (c > j) b = mid; else a = mid;
         }
         lamall[(size_t)s * N + (N - 1 - j)] = 0.5 * (a + b);

@@ -170,47 +170,71 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
     }
 }
 
-// grid = (ceil(N / 8), S): one warp per output row. r_i = lbar + sum_s c_s v_si^2 is the diagonal of the clipped matrix.
+// grid = (ceil(N / 32), S), 256 threads: the CTA stages the signal eigenvectors in shared memory once (they are re-read
+// N / 32 times per simulation instead of N / 8 from L2), each warp owns 4 output rows and a lane walks the columns, so one
+// shared-memory load of v_sj feeds 4 FMAs.  r_i = lbar + sum_s c_s v_si^2 is the diagonal of the clipped matrix.
+#define RC_ROWS 4
 __global__ void __launch_bounds__(256) reconstruct_kernel(const double* __restrict__ V, const double* __restrict__ lamall,
                                                           const int* __restrict__ nfall,
                                                           const double* __restrict__ sigmaall, int N,
                                                           double* __restrict__ covall) {
     extern __shared__ double sm[];
     double* rs = sm;             // [N] sqrt(r_j)
-    double* coef = sm + N;       // [EV3_VMAX]
+    double* sg = sm + N;         // [N] sigma_j
+    double* coef = sg + N;       // [EV3_VMAX]
+    double* Vsm = coef + EV3_VMAX;   // [nf][N]
     __shared__ double red[32];
     const int sim = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nf = nfall[sim];
     if (nf > EV3_VMAX) return;   // left to eigvec_kernel
     const double* lam = lamall + (size_t)sim * N;
-    const double* sigma = sigmaall + (size_t)sim * N;
     const double* Vs = V + (size_t)sim * EV3_VMAX * N;
     double part = 0.0;
     for (int i = nf + tid; i < N; i += 256) part += lam[i];
+    for (int idx = tid; idx < nf * N; idx += 256) Vsm[idx] = Vs[idx];
+    for (int j = tid; j < N; j += 256) sg[j] = sigmaall[(size_t)sim * N + j];
     const double lbar = (nf < N) ? block_sum(part, red) / (double)(N - nf) : 0.0;
     if (tid < EV3_VMAX) coef[tid] = (tid < nf) ? lam[tid] - lbar : 0.0;
     __syncthreads();
     for (int j = tid; j < N; j += 256) {
         double r = lbar;
-        for (int s = 0; s < nf; ++s) { const double v = Vs[(size_t)s * N + j]; r = fma(coef[s] * v, v, r); }
+        for (int s = 0; s < nf; ++s) { const double v = Vsm[s * N + j]; r = fma(coef[s] * v, v, r); }
         rs[j] = sqrt(r);
     }
     __syncthreads();
-    const int i = blockIdx.x * 8 + wid;
-    if (i >= N) return;
-    double vi[EV3_VMAX];
+    const int i0 = blockIdx.x * 32 + wid * RC_ROWS;
+    if (i0 >= N) return;
+    double a[RC_ROWS][EV3_VMAX], rsi[RC_ROWS], si[RC_ROWS];
 #pragma unroll
-    for (int s = 0; s < EV3_VMAX; ++s) vi[s] = (s < nf) ? coef[s] * Vs[(size_t)s * N + i] : 0.0;
-    const double rsi = rs[i], si = sigma[i];
-    double* out = covall + (size_t)sim * N * N + (size_t)i * N;
+    for (int r = 0; r < RC_ROWS; ++r) {
+        const int i = min(i0 + r, N - 1);
+        rsi[r] = rs[i];
+        si[r] = sg[i];
+#pragma unroll
+        for (int s = 0; s < EV3_VMAX; ++s) a[r][s] = (s < nf) ? coef[s] * Vsm[s * N + i] : 0.0;
+    }
+    double* out = covall + (size_t)sim * N * N;
     for (int j = lane; j < N; j += 32) {
-        double acc = (i == j) ? lbar : 0.0;
+        double acc[RC_ROWS];
 #pragma unroll
-        for (int s = 0; s < EV3_VMAX; ++s)
-            if (s < nf) acc = fma(vi[s], Vs[(size_t)s * N + j], acc);
-        double r = acc / (rsi * rs[j]);
-        r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-        out[j] = r * (si * sigma[j]);
+        for (int r = 0; r < RC_ROWS; ++r) acc[r] = (i0 + r == j) ? lbar : 0.0;
+#pragma unroll
+        for (int s = 0; s < EV3_VMAX; ++s) {
+            if (s < nf) {
+                const double v = Vsm[s * N + j];
+#pragma unroll
+                for (int r = 0; r < RC_ROWS; ++r) acc[r] = fma(a[r][s], v, acc[r]);
+            }
+        }
+        const double rsj = rs[j], sj = sg[j];
+#pragma unroll
+        for (int r = 0; r < RC_ROWS; ++r) {
+            if (i0 + r < N) {
+                double c = acc[r] / (rsi[r] * rsj);
+                c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+                out[(size_t)(i0 + r) * N + j] = c * (si[r] * sj);
+            }
+        }
     }
 }
 
@@ -238,8 +262,9 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
     else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
-    const size_t smem = (n + EV3_VMAX) * sizeof(double);
-    reconstruct_kernel<<<dim3((N + 7) / 8, S), 256, smem, ctx->stream>>>(V, lam, nf, sigma, N, cov);
+    const size_t smem = (2 * n + EV3_VMAX + EV3_VMAX * n) * sizeof(double);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reconstruct_kernel<<<dim3((N + 31) / 32, S), 256, smem, ctx->stream>>>(V, lam, nf, sigma, N, cov);
     MCOSB_LAUNCHED(ctx, MK_RECONSTRUCT);
     return 1;
 }

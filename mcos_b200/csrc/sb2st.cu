@@ -18,8 +18,27 @@
 // W warps work on one matrix as a software pipeline: warp u owns sweeps s = u (mod W) and may run step k of sweep s once
 // sweep s - 1 has completed step k + 2 (the two then touch disjoint elements); progress is published through shared
 // memory.  The reflectors go to Q2[s][lo - s - 1 + m] (tau in the slot of the implicit 1) for q2back_kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sbr.cuh"
+
+// 1/x and 1/sqrt(x) to ~1 ulp: hardware approximation (2^-23) + two Newton steps
+__device__ __forceinline__ double sbr_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ double sbr_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    return r;
+}
 
 template <int W>
 __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict__ Aall, int N, double* __restrict__ dall,
@@ -54,21 +73,18 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
     int seen = -1;   // last progress value read from the predecessor
 
     for (int s = u; s + 2 < N; s += W) {
+        double xn[8];                             // first column of the next bulge, handed on in registers
         for (int k = 0;; ++k) {
             const int lo = s + 1 + 8 * k;
             if (N - lo < 2) break;
             if (s > 0) {
                 int need_done = k + 3;
                 if (need_done > 255) need_done = 255;
-                const int need = (s - 1) * 256 + need_done;
+                const int need = (s - 1) * 256 + need_done;   // the predecessor publishes ..255 when its sweep is complete
                 if (seen < need) {
                     if (lane == 0) {
                         int cur = prog[pu];
-                        // the predecessor publishes 255 when its sweep is complete
-                        while (cur < need && !(cur >= (s - 1) * 256 + 255)) {
-                            __nanosleep(40);
-                            cur = prog[pu];
-                        }
+                        while (cur < need) cur = prog[pu];
                         seen = cur;
                     }
                     seen = __shfl_sync(0xffffffffu, seen, 0);
@@ -86,41 +102,59 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
                 if (dead) z[m] = 0.0;
             }
             double x[8];
+            if (k == 0) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) x[m] = __shfl_sync(0xffffffffu, z[m], 0);
-            double ss = 0.0;
+                for (int m = 0; m < 8; ++m) x[m] = __shfl_sync(0xffffffffu, z[m], 0);
+            } else {
 #pragma unroll
-            for (int m = 1; m < 8; ++m) ss = fma(x[m], x[m], ss);
-            const double alpha = x[0];
-            double tau = 0.0, scale = 0.0, beta = alpha;
-            if (ss > 0.0) {
-                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-                tau = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+                for (int m = 0; m < 8; ++m) x[m] = xn[m];
             }
-            double v[8];
-            v[0] = 1.0;
+            // Householder in unnormalised form H = I - gam u u', u = (alpha - beta, x_1 .. x_7): only one rsqrt and one
+            // reciprocal sit on the critical path (IEEE sqrt and two divisions cost ~350 cycles)
+            const double ss = (x[1] * x[1] + x[2] * x[2]) + (x[3] * x[3] + x[4] * x[4]) +
+                              ((x[5] * x[5] + x[6] * x[6]) + x[7] * x[7]);
+            const double alpha = x[0];
+            double gam = 0.0, tau = 0.0, scale = 0.0, beta = alpha, u0 = 0.0;
+            if (ss > 1e-280) {
+                const double n2 = fma(alpha, alpha, ss);
+                const double rs = sbr_rsqrt(n2);
+                const double tt = fma(fabs(alpha), rs, 1.0);          // tau = (beta - alpha) / beta
+                const double rt = sbr_rcp(tt);
+                beta = -copysign(n2 * rs, alpha);
+                u0 = alpha - beta;
+                gam = rs * rs * rt;                                   // 1 / (nrm (nrm + |alpha|))
+                scale = copysign(rs * rt, alpha);                     // 1 / u0
+                tau = tt;
+            }
+            double uv[8];
+            uv[0] = u0;
 #pragma unroll
-            for (int m = 1; m < 8; ++m) v[m] = x[m] * scale;
-            double dot = 0.0;
+            for (int m = 1; m < 8; ++m) uv[m] = x[m];
+            double dot = ((uv[1] * z[1] + uv[2] * z[2]) + (uv[3] * z[3] + uv[4] * z[4])) +
+                         ((uv[5] * z[5] + uv[6] * z[6]) + uv[7] * z[7]);
+            dot = fma(u0, z[0], dot);
+            const double p = gam * dot;
+            double ur = uv[0];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) dot = fma(v[m], z[m], dot);
-            const double p = tau * dot;
-            double vr = v[0];
+            for (int m = 1; m < 8; ++m) ur = (l == m) ? uv[m] : ur;
+            // the right application's first column is the next reflector's x: hand it on before anything else
+            {
+                const double z0new = fma(-p, u0, z[0]);
 #pragma unroll
-            for (int m = 1; m < 8; ++m) vr = (l == m) ? v[m] : vr;
-            double kp = vr * p;
+                for (int m = 0; m < 8; ++m) xn[m] = __shfl_sync(0xffffffffu, z0new, 16 + m);
+            }
+            double kp = ur * p;
             kp += __shfl_xor_sync(0xffffffffu, kp, 1);
             kp += __shfl_xor_sync(0xffffffffu, kp, 2);
             kp += __shfl_xor_sync(0xffffffffu, kp, 4);
-            const double wr = fma(-0.5 * tau * kp, vr, p);
-            const double a1 = g1 ? vr : p;
+            const double wr = fma(-0.5 * gam * kp, ur, p);
+            const double a1 = g1 ? ur : p;
             const double a2 = g1 ? wr : 0.0;
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 const double wm = __shfl_sync(0xffffffffu, wr, 8 + m);
-                const double b1 = g1 ? wm : v[m];
-                z[m] = fma(-a2, v[m], fma(-a1, b1, z[m]));
+                const double b1 = g1 ? wm : uv[m];
+                z[m] = fma(-a2, uv[m], fma(-a1, b1, z[m]));
             }
             if (g0 && l == 0) {
                 z[0] = beta;
@@ -137,7 +171,7 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
             if (lane < 8 && lo + lane < N) {
                 double q = tau;
 #pragma unroll
-                for (int m = 1; m < 8; ++m) q = (lane == m) ? v[m] : q;
+                for (int m = 1; m < 8; ++m) q = (lane == m) ? x[m] * scale : q;
                 Q2[(size_t)s * N + (lo - s - 1) + lane] = q;
             }
             __syncwarp();
@@ -160,9 +194,21 @@ int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double
     const int N = ctx->N;
     const size_t smem = (size_t)(N + 16) * 16 * sizeof(double);
     if (smem + 1024 > (size_t)ctx->smem_optin || N > 768) return 0;
-    constexpr int W = 4;
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sb2st_kernel<W><<<S, W * 32, smem, ctx->stream>>>(A, N, d, e, Q2);
+    static int Wsel = -1;
+    if (Wsel < 0) {
+        const char* e = getenv("MCOSB_SB2ST_W");
+        Wsel = e ? atoi(e) : 4;
+    }
+#define SB2ST_LAUNCH(W)                                                                                               \
+    do {                                                                                                              \
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        sb2st_kernel<W><<<S, W * 32, smem, ctx->stream>>>(A, N, d, e, Q2);                                            \
+    } while (0)
+    if (Wsel == 1) SB2ST_LAUNCH(1);
+    else if (Wsel == 2) SB2ST_LAUNCH(2);
+    else if (Wsel == 8) SB2ST_LAUNCH(8);
+    else SB2ST_LAUNCH(4);
+#undef SB2ST_LAUNCH
     MCOSB_LAUNCHED(ctx, MK_SB2ST);
     return 1;
 }
