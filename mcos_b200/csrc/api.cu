@@ -118,6 +118,7 @@ extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* c
     int flag = 0;
     MCOSB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ideal_key.clear();  // ideal allocations belong to the previous truth
     ctx->have_truth = true;  // mu/cov are usable by the estimators even if sampling is not
     if (flag) return mcosb_fail(ctx, MCOSB_ERR_NOT_PD, "true covariance is not positive definite");
     return MCOSB_OK;

@@ -110,6 +110,8 @@ struct mcosb_ctx {
     double stage_ms[MCOSB_N_STAGES] = {};
     int smem_optin = 0;
     int num_sms = MCOSB_SMS;
+    std::string ideal_key;  // optimizer list whose ideal allocations (on the current truth) sit in SL_IDEAL
+    size_t mem_budget = 0;  // free HBM + context-held scratch at the first mcosb_run (wave sizing)
     int eig_method = 0;  // 0 auto, 1 one-stage Householder (tridiag / tridiag2), 2 two-stage (sy2sb + sb2st)
     // per-kernel timing (mcosb_set_profiling): one event after every launch; a kernel's time is the gap to the
     // previous event on the stream

@@ -2,6 +2,8 @@
 // the device, in waves sized to HBM.  The ideal allocation optimizer.allocate(true mu, true cov) (mcos.py:30) is
 // loop-invariant and computed once per call instead of once per simulation.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -89,6 +91,9 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     for (int i = 0; i < MCOSB_N_STAGES; ++i) ctx->stage_ms[i] = 0.0;
     if (S == 0) return MCOSB_OK;
 
+    static const bool trace = getenv("MCOSB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     Staging st(ctx);
     double* derr;
     int* dstatus;
@@ -98,35 +103,49 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     MCOSB_CUDA(ctx, cudaMemsetAsync(dstatus, 0, (size_t)S * sizeof(int), ctx->stream));
 
     MCOSB_PROFILE_MARK(ctx);
-    // ---- ideal allocations on the true (mu, cov), once ------------------------------------------------------------------
+    // ---- ideal allocations on the true (mu, cov): once per (truth, optimizer list), kept in the context -----------------
     double* d_ideal;
     int* d_ideal_status;
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_IDEAL, (size_t)nopt * N + 8, &d_ideal));
-    d_ideal_status = reinterpret_cast<int*>(d_ideal + (size_t)nopt * N);
-    MCOSB_CUDA(ctx, cudaMemsetAsync(d_ideal_status, 0, sizeof(int), ctx->stream));
-    for (int o = 0; o < nopt; ++o) {
-        double* wi = d_ideal + (size_t)o * N;
-        const int kind = plan->optimizers[o];
-        if (kind == MCOSB_OPT_MARKOWITZ)
-            MCOSB_TRY(mcosb_dev_markowitz(ctx, 1, ctx->d_mu, ctx->d_cov, plan->risk_free_rate, 1, wi, nullptr, d_ideal_status));
-        else if (kind == MCOSB_OPT_HRP)
-            MCOSB_TRY(mcosb_dev_hrp(ctx, 1, ctx->d_cov, wi, nullptr, nullptr, d_ideal_status));
-        else if (kind == MCOSB_OPT_RISK_PARITY)
-            MCOSB_TRY(mcosb_dev_risk_parity(ctx, 1, ctx->d_cov, nullptr, wi, nullptr, d_ideal_status));
-        else
-            MCOSB_TRY(mcosb_dev_nco(ctx, 1, ctx->d_mu, ctx->d_cov, plan->nco_max_clusters, plan->nco_trials, nullptr, wi,
-                                    nullptr, d_ideal_status));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_IDEAL, (size_t)4 * N + 8, &d_ideal));
+    d_ideal_status = reinterpret_cast<int*>(d_ideal + (size_t)4 * N);
+    char key[160];
+    snprintf(key, sizeof key, "%d|%d,%d,%d,%d|%.17g|%d|%d", nopt, plan->optimizers[0], plan->optimizers[1],
+             plan->optimizers[2], plan->optimizers[3], plan->risk_free_rate, plan->nco_max_clusters, plan->nco_trials);
+    if (ctx->ideal_key != key) {
+        ctx->ideal_key.clear();
+        MCOSB_CUDA(ctx, cudaMemsetAsync(d_ideal_status, 0, sizeof(int), ctx->stream));
+        for (int o = 0; o < nopt; ++o) {
+            double* wi = d_ideal + (size_t)o * N;
+            const int kind = plan->optimizers[o];
+            if (kind == MCOSB_OPT_MARKOWITZ)
+                MCOSB_TRY(mcosb_dev_markowitz(ctx, 1, ctx->d_mu, ctx->d_cov, plan->risk_free_rate, 1, wi, nullptr, d_ideal_status));
+            else if (kind == MCOSB_OPT_HRP)
+                MCOSB_TRY(mcosb_dev_hrp(ctx, 1, ctx->d_cov, wi, nullptr, nullptr, d_ideal_status));
+            else if (kind == MCOSB_OPT_RISK_PARITY)
+                MCOSB_TRY(mcosb_dev_risk_parity(ctx, 1, ctx->d_cov, nullptr, wi, nullptr, d_ideal_status));
+            else
+                MCOSB_TRY(mcosb_dev_nco(ctx, 1, ctx->d_mu, ctx->d_cov, plan->nco_max_clusters, plan->nco_trials, nullptr, wi,
+                                        nullptr, d_ideal_status));
+        }
+        ctx->ideal_key = key;
     }
 
+    const double t_ideal = now();
     // ---- wave size from free HBM -----------------------------------------------------------------------------------------
     int wave = plan->wave;
     if (wave <= 0) {
-        size_t free_b = 0, total_b = 0;
-        MCOSB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        // cudaMemGetInfo takes 0.1 - 40 ms on this platform and would leave the GPU idle between the ideal allocation and
+        // the first wave: ask once per context and remember (free + what the context already holds)
         size_t held = 0;
         for (int i = 0; i < SL_COUNT; ++i) held += ctx->slot_bytes[i];
+        if (ctx->mem_budget == 0) {
+            size_t free_once = 0, total_b = 0;
+            MCOSB_CUDA(ctx, cudaMemGetInfo(&free_once, &total_b));
+            ctx->mem_budget = free_once + held;
+        }
+        const size_t free_b = ctx->mem_budget > held ? ctx->mem_budget - held : 0;
         // per simulation: cov + denoise work matrix + HRP D and E (4 N^2), inverse-iteration scratch, small vectors
-        size_t per_sim = (4 * N * N + 6 * N * 16 + 16 * N) * sizeof(double);
+        size_t per_sim = (5 * N * N + 6 * N * 16 + 16 * N) * sizeof(double);
         size_t budget = (free_b + held) / 2;
         size_t fixed = 2 * ((size_t)1 << 30) + ((size_t)1 << 28);  // X + Z chunk buffers
         size_t w = budget > fixed ? (budget - fixed) / per_sim : 1;
@@ -134,6 +153,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     }
     wave = std::min(wave, S);
 
+    const double t_mem = now();
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> marks;
     int rc = MCOSB_OK;
     for (int s0 = 0; s0 < S && rc == MCOSB_OK; s0 += wave) {
@@ -141,7 +161,9 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
         rc = mcosb_run_wave(ctx, plan, sim_id0 + s0, W, d_ideal, derr + (size_t)s0 * nopt, dstatus + s0, marks);
     }
     if (rc == MCOSB_OK) rc = st.finish();
+    const double t_launched = now();
     cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    const double t_synced = now();
     for (auto& m : marks) {
         if (m.second.first && m.second.second && se == cudaSuccess) {
             float ms = 0.f;
@@ -154,6 +176,9 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     if (se != cudaSuccess) return mcosb_fail(ctx, MCOSB_ERR_CUDA, cudaGetErrorString(se));
     int ideal_status = 0;
     MCOSB_CUDA(ctx, cudaMemcpy(&ideal_status, d_ideal_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (trace)
+        fprintf(stderr, "mcosb_run host ms: ideal-launch %.2f memgetinfo %.2f wave-launch %.2f sync-wait %.2f tail %.2f\n",
+                t_ideal - t_start, t_mem - t_ideal, t_launched - t_mem, t_synced - t_launched, now() - t_synced);
     if (ideal_status) {
         char buf[128];
         snprintf(buf, sizeof buf, "ideal allocation on the true (mu, cov) failed with status bits %d", ideal_status);
