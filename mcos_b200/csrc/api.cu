@@ -70,31 +70,40 @@ extern "C" int mcosb_last_stage_ms(mcosb_ctx* ctx, double* stage_ms) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One-off Cholesky of the true covariance (single CTA, right-looking, in place on a copy). Runs once per truth.
+// Cholesky of the true covariance (single CTA, in place on a copy), once per truth -- but the end-to-end path uploads
+// the truth with every call, so it is not free.  Left-looking by columns: row k of L is staged in shared memory, every
+// warp forms the dot products L[i][:k] . L[k][:k] of its rows with coalesced reads (N^3 / 6 FMA, no trailing update
+// through global memory: the right-looking version took 11 ms at N = 500).
 // flag[0] is set to 1 when a pivot is not positive.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) chol_truth_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
+    extern __shared__ double Lk[];   // [n] row k of L
     __shared__ double s_piv;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int k = 0; k < n; ++k) {
-        if (threadIdx.x == 0) {
-            double d = L[(size_t)k * n + k];
-            if (!(d > 0.0)) { flag[0] = 1; d = 1.0; }
-            s_piv = sqrt(d);
-            L[(size_t)k * n + k] = s_piv;
+        for (int j = tid; j < k; j += 1024) Lk[j] = L[(size_t)k * n + j];
+        __syncthreads();
+        for (int i = k + w; i < n; i += 32) {
+            const double* row = L + (size_t)i * n;
+            double dot = 0.0;
+            for (int j = lane; j < k; j += 32) dot = fma(row[j], Lk[j], dot);
+            dot = warp_sum(dot);
+            if (lane == 0) {
+                double v = row[k] - dot;
+                if (i == k) {
+                    if (!(v > 0.0)) { flag[0] = 1; v = 1.0; }
+                    v = sqrt(v);
+                    s_piv = v;
+                }
+                L[(size_t)i * n + k] = v;
+            }
         }
         __syncthreads();
-        double piv = s_piv;
-        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) L[(size_t)i * n + k] /= piv;
-        __syncthreads();
-        // trailing update of the lower triangle: L[i][j] -= L[i][k] * L[j][k], k < j <= i
-        int m = n - k - 1;
-        for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
-            int i = k + 1 + idx / m, j = k + 1 + idx % m;
-            if (j <= i) L[(size_t)i * n + j] -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
-        }
+        const double piv = s_piv;
+        for (int i = k + 1 + tid; i < n; i += 1024) L[(size_t)i * n + k] /= piv;
         __syncthreads();
     }
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    for (int idx = tid; idx < n * n; idx += 1024) {
         int i = idx / n, j = idx % n;
         if (j > i) L[idx] = 0.0;
     }
@@ -113,7 +122,7 @@ extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* c
     int* dflag = nullptr;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, 1, &dflag));
     MCOSB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
-    chol_truth_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_chol, ctx->N, dflag);
+    chol_truth_kernel<<<1, 1024, n * sizeof(double), ctx->stream>>>(ctx->d_chol, ctx->N, dflag);
     MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
     int flag = 0;
     MCOSB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
