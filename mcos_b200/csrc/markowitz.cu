@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(MK_THREADS) markowitz_kernel(const double* __r
                                                                const double* __restrict__ cov_all, int N, int fcap,
                                                                double rf, int clean, int max_iter,
                                                                double* __restrict__ w_all, int* __restrict__ iters_out,
-                                                               int* __restrict__ status) {
+                                                               int* __restrict__ status, int* __restrict__ capflag,
+                                                               int pass) {
+    // two tiers: pass 0 runs everything with a small free-set capacity (30 KB of shared memory -> 7 CTAs per SM instead
+    // of 2; the free set is ~50 at N = 500), pass 1 re-solves with the full capacity only what overflowed
+    if (pass == 1 && capflag[blockIdx.x] == 0) return;
     extern __shared__ double sm[];
     MkSmem s;
     s.c = sm;
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(MK_THREADS) markowitz_kernel(const double* __r
     const double* C = cov_all + (size_t)sim * N * N;
     double* w = w_all + (size_t)sim * N;
     int st = 0;
+    bool redo = false;
 
     // start vertex: best stand-alone Sharpe ratio among assets with c_i > 0
     double best = INFINITY;
@@ -233,7 +238,11 @@ __global__ void __launch_bounds__(MK_THREADS) markowitz_kernel(const double* __r
             int enter;
             block_argmin(lmin, imin, s, lv, enter);
             if (enter >= N || lv >= -1e-12 * fmax(1.0, fabs(nu))) break;  // KKT satisfied
-            if (f >= fcap) { st |= MCOSB_ST_QP_CAP; break; }
+            if (f >= fcap) {
+                if (pass == 0 && capflag) { if (tid == 0) capflag[sim] = 1; redo = true; }
+                else st |= MCOSB_ST_QP_CAP;
+                break;
+            }
             if (tid == 0) s.F[f] = enter;
             __syncthreads();
             if (!chol_append(s, C, N, f, enter)) st |= MCOSB_ST_NOT_PD;
@@ -270,6 +279,7 @@ __global__ void __launch_bounds__(MK_THREADS) markowitz_kernel(const double* __r
             if (!chol_refactor(s, C, N, f)) st |= MCOSB_ST_NOT_PD;
         }
     }
+    if (redo) return;   // pass 1 solves this simulation again with the full capacity
     // w = y / sum(y); clean_weights: |w| < 1e-4 -> 0, round half-even to 5 decimals, no renormalisation
     double part = 0.0;
     for (int i = tid; i < N; i += MK_THREADS) part += s.y[i];
@@ -295,12 +305,26 @@ int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* 
     if (S == 0) return MCOSB_OK;
     const int N = ctx->N;
     const int fcap = mk_fcap(N);
-    size_t smem = (3 * (size_t)N + 2 * fcap + (size_t)fcap * (fcap + 1) / 2 + 32) * sizeof(double) +
-                  ((size_t)fcap + 64) * sizeof(int);
+    auto smem_of = [&](int cap) {
+        return (3 * (size_t)N + 2 * cap + (size_t)cap * (cap + 1) / 2 + 32) * sizeof(double) + ((size_t)cap + 64) * sizeof(int);
+    };
+    const size_t smem = smem_of(fcap);
     if (smem > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for markowitz_kernel");
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(markowitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    markowitz_kernel<<<S, MK_THREADS, smem, ctx->stream>>>(dmu, dcov, N, fcap, rf, clean, 50 * N + 100, dw, diters,
-                                                          dstatus);
+    const int fcap0 = 64;
+    if (fcap > fcap0 && S > 1) {
+        int* capflag;
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_MK_ITERS, (size_t)S, &capflag));
+        MCOSB_CUDA(ctx, cudaMemsetAsync(capflag, 0, (size_t)S * sizeof(int), ctx->stream));
+        markowitz_kernel<<<S, MK_THREADS, smem_of(fcap0), ctx->stream>>>(dmu, dcov, N, fcap0, rf, clean, 50 * N + 100, dw,
+                                                                        diters, dstatus, capflag, 0);
+        MCOSB_LAUNCHED(ctx, MK_MARKOWITZ);
+        markowitz_kernel<<<S, MK_THREADS, smem, ctx->stream>>>(dmu, dcov, N, fcap, rf, clean, 50 * N + 100, dw, diters,
+                                                              dstatus, capflag, 1);
+    } else {
+        markowitz_kernel<<<S, MK_THREADS, smem, ctx->stream>>>(dmu, dcov, N, fcap, rf, clean, 50 * N + 100, dw, diters,
+                                                              dstatus, nullptr, 2);
+    }
     MCOSB_LAUNCHED(ctx, MK_MARKOWITZ);
     return MCOSB_OK;
 }
