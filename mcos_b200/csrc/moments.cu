@@ -174,13 +174,13 @@ __global__ void __launch_bounds__(256) lw_rownorm_kernel(const double* __restric
     if (threadIdx.x == 0) part[(size_t)s * gridDim.x + blockIdx.x] = tot;
 }
 
-// Finishes Ledoit-Wolf: shrinkage from the partials, then cov <- (1-d) cov + d m I in place.  grid = S
+// Finishes Ledoit-Wolf: shrinkage from the partials, then cov <- (1-d) cov + d m I in place.  grid = (S, 8)
 __global__ void __launch_bounds__(256) lw_finish_kernel(double* __restrict__ cov, const double* __restrict__ lwpart,
                                                         int ntiles, const double* __restrict__ rnpart, int nchunks,
                                                         int T, int N, double* __restrict__ shrink_out) {
     __shared__ double s_shrink, s_m;
     const int s = blockIdx.x;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {   // every CTA of the matrix repeats this small sum in the same order
         double delta_raw = 0.0, tr = 0.0, beta_raw = 0.0;
         for (int i = 0; i < ntiles; ++i) {
             delta_raw += lwpart[((size_t)s * ntiles + i) * 2];
@@ -194,15 +194,21 @@ __global__ void __launch_bounds__(256) lw_finish_kernel(double* __restrict__ cov
         double sh = (beta == 0.0) ? 0.0 : beta / delta;
         s_shrink = sh;
         s_m = m;
-        if (shrink_out) shrink_out[s] = sh;
+        if (shrink_out && blockIdx.y == 0) shrink_out[s] = sh;
     }
     __syncthreads();
     const double sh = s_shrink, m = s_m;
     double* c = cov + (size_t)s * N * N;
-    for (size_t idx = threadIdx.x; idx < (size_t)N * N; idx += blockDim.x) {
-        double v = (1.0 - sh) * c[idx];
-        if (idx / N == idx % N) v += sh * m;
-        c[idx] = v;
+    // rows blockIdx.y, blockIdx.y + gridDim.y, ...: one warp per row (a single CTA per matrix streamed 4 MB through
+    // 256 threads with a 64-bit div/mod per element and took 0.29 ms per 128 matrices)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = blockIdx.y * nw + wid; i < N; i += gridDim.y * nw) {
+        double* row = c + (size_t)i * N;
+        for (int j = lane; j < N; j += 32) {
+            double v = (1.0 - sh) * row[j];
+            if (j == i) v += sh * m;
+            row[j] = v;
+        }
     }
 }
 
@@ -239,7 +245,7 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWSTAT, (size_t)S * nchunks, &rnpart));
         lw_rownorm_kernel<<<dim3(nchunks, S), 256, 0, ctx->stream>>>(dX, dmu, T, N, rnpart);
         MCOSB_LAUNCHED(ctx, MK_LW_ROWNORM);
-        lw_finish_kernel<<<S, 256, 0, ctx->stream>>>(dcov, lwpart, ntiles, rnpart, nchunks, T, N, dshrink);
+        lw_finish_kernel<<<dim3(S, 8), 256, 0, ctx->stream>>>(dcov, lwpart, ntiles, rnpart, nchunks, T, N, dshrink);
         MCOSB_LAUNCHED(ctx, MK_LW_FINISH);
     } else if (dshrink) {
         fill_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(dshrink, (size_t)S, 0.0);

@@ -69,11 +69,14 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
         else off[m] = m * 16 + 8 + l - m;
     }
     const bool g0 = grp == 0, g1 = grp == 1;
+    // which of its 8 values a lane stores: group 0 and 2 all, group 1 the lower part of its row, group 3 nothing
+    const unsigned smask = (grp == 3) ? 0u : (g1 ? ((2u << l) - 1u) : 0xffu);
     const int pu = (u + W - 1) % W;
     int seen = -1;   // last progress value read from the predecessor
 
     for (int s = u; s + 2 < N; s += W) {
         double xn[8];                             // first column of the next bulge, handed on in registers
+        double unext = 0.0;                       // x[l] of the next step for this lane (u_r of the rank-2 update)
         for (int k = 0;; ++k) {
             const int lo = s + 1 + 8 * k;
             if (N - lo < 2) break;
@@ -92,22 +95,23 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
                 }
             }
             const int base = lo * 16;
-            const bool k0 = (k == 0) && g0;
-            const bool dead = (k0 && l != 0) || grp == 3;
+            const bool first = (k == 0);
+            // step 0 has no block left of the window: group 0 reads (and ignores) valid data one block further down
+            const int zb = (first && g0) ? base + 128 : base;
             double z[8];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int o = k0 ? (m - 15) : off[m];
-                z[m] = Bs[base + o];
-                if (dead) z[m] = 0.0;
-            }
-            double x[8];
-            if (k == 0) {
+            for (int m = 0; m < 8; ++m) z[m] = Bs[zb + off[m]];
+            double x[8], ur;
+            if (first) {
 #pragma unroll
-                for (int m = 0; m < 8; ++m) x[m] = __shfl_sync(0xffffffffu, z[m], 0);
+                for (int m = 0; m < 8; ++m) x[m] = Bs[base - 15 + m];       // column s below the diagonal
+                ur = x[0];
+#pragma unroll
+                for (int m = 1; m < 8; ++m) ur = (l == m) ? x[m] : ur;
             } else {
 #pragma unroll
                 for (int m = 0; m < 8; ++m) x[m] = xn[m];
+                ur = unext;
             }
             // Householder in unnormalised form H = I - gam u u', u = (alpha - beta, x_1 .. x_7): only one rsqrt and one
             // reciprocal sit on the critical path (IEEE sqrt and two divisions cost ~350 cycles)
@@ -126,54 +130,51 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
                 scale = copysign(rs * rt, alpha);                     // 1 / u0
                 tau = tt;
             }
-            double uv[8];
-            uv[0] = u0;
-#pragma unroll
-            for (int m = 1; m < 8; ++m) uv[m] = x[m];
-            double dot = ((uv[1] * z[1] + uv[2] * z[2]) + (uv[3] * z[3] + uv[4] * z[4])) +
-                         ((uv[5] * z[5] + uv[6] * z[6]) + uv[7] * z[7]);
+            if (l == 0) ur = u0;
+            double dot = ((x[1] * z[1] + x[2] * z[2]) + (x[3] * z[3] + x[4] * z[4])) +
+                         ((x[5] * z[5] + x[6] * z[6]) + x[7] * z[7]);
             dot = fma(u0, z[0], dot);
             const double p = gam * dot;
-            double ur = uv[0];
-#pragma unroll
-            for (int m = 1; m < 8; ++m) ur = (l == m) ? uv[m] : ur;
             // the right application's first column is the next reflector's x: hand it on before anything else
             {
                 const double z0new = fma(-p, u0, z[0]);
 #pragma unroll
                 for (int m = 0; m < 8; ++m) xn[m] = __shfl_sync(0xffffffffu, z0new, 16 + m);
+                unext = __shfl_sync(0xffffffffu, z0new, 16 + l);
             }
             double kp = ur * p;
             kp += __shfl_xor_sync(0xffffffffu, kp, 1);
             kp += __shfl_xor_sync(0xffffffffu, kp, 2);
             kp += __shfl_xor_sync(0xffffffffu, kp, 4);
             const double wr = fma(-0.5 * gam * kp, ur, p);
-            const double a1 = g1 ? ur : p;
-            const double a2 = g1 ? wr : 0.0;
+            // z -= ca u + cb w:  groups 0 / 2: ca = gam (u . z), cb = 0;  group 1 (row r of D): ca = w_r, cb = u_r
+            const double ca = g1 ? wr : p;
+            const double cb = g1 ? ur : 0.0;
+            z[0] = fma(-cb, __shfl_sync(0xffffffffu, wr, 8), fma(-ca, u0, z[0]));
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const double wm = __shfl_sync(0xffffffffu, wr, 8 + m);
-                const double b1 = g1 ? wm : uv[m];
-                z[m] = fma(-a2, uv[m], fma(-a1, b1, z[m]));
-            }
-            if (g0 && l == 0) {
-                z[0] = beta;
+            for (int m = 1; m < 8; ++m) z[m] = fma(-cb, __shfl_sync(0xffffffffu, wr, 8 + m), fma(-ca, x[m], z[m]));
+            if (first) {
+                if (lane == 0) {                                   // column s: (beta, 0, ..., 0)
+                    Bs[base - 15] = beta;
 #pragma unroll
-                for (int m = 1; m < 8; ++m) z[m] = 0.0;
-            }
-            if (!dead) {
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const int o = k0 ? (m - 15) : off[m];
-                    if (!g1 || m <= l) Bs[base + o] = z[m];
+                    for (int m = 1; m < 8; ++m) Bs[base - 15 + m] = 0.0;
                 }
-            }
-            if (lane < 8 && lo + lane < N) {
-                double q = tau;
+                if (!g0) {
 #pragma unroll
-                for (int m = 1; m < 8; ++m) q = (lane == m) ? x[m] * scale : q;
-                Q2[(size_t)s * N + (lo - s - 1) + lane] = q;
+                    for (int m = 0; m < 8; ++m)
+                        if ((smask >> m) & 1u) Bs[base + off[m]] = z[m];
+                }
+            } else {
+                if (lane == 0) {
+                    z[0] = beta;
+#pragma unroll
+                    for (int m = 1; m < 8; ++m) z[m] = 0.0;
+                }
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if ((smask >> m) & 1u) Bs[base + off[m]] = z[m];
             }
+            if (lane < 8 && lo + lane < N) Q2[(size_t)s * N + (lo - s - 1) + lane] = (lane == 0) ? tau : ur * scale;
             __syncwarp();
             __threadfence_block();
             if (lane == 0) prog[u] = s * 256 + k + 1;
