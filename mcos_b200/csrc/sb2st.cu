@@ -40,6 +40,16 @@ __device__ __forceinline__ double sbr_rsqrt(double x) {
     return r;
 }
 
+// predicated shared-memory store without a branch
+__device__ __forceinline__ void sbr_st_if(double* p, double v, unsigned pred) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(a), "d"(v), "r"(pred) : "memory");
+}
+
+// acquire/release fence at CTA scope: orders the band updates against the progress flag (the sequentially consistent
+// __threadfence_block is not needed)
+__device__ __forceinline__ void sbr_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
 template <int W>
 __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict__ Aall, int N, double* __restrict__ dall,
                                                        double* __restrict__ eall, double* __restrict__ Q2all) {
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
                         seen = cur;
                     }
                     seen = __shfl_sync(0xffffffffu, seen, 0);
-                    __threadfence_block();
+                    sbr_fence_cta();
                 }
             }
             const int base = lo * 16;
@@ -161,8 +171,7 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
                 }
                 if (!g0) {
 #pragma unroll
-                    for (int m = 0; m < 8; ++m)
-                        if ((smask >> m) & 1u) Bs[base + off[m]] = z[m];
+                    for (int m = 0; m < 8; ++m) sbr_st_if(&Bs[base + off[m]], z[m], (smask >> m) & 1u);
                 }
             } else {
                 if (lane == 0) {
@@ -171,12 +180,11 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
                     for (int m = 1; m < 8; ++m) z[m] = 0.0;
                 }
 #pragma unroll
-                for (int m = 0; m < 8; ++m)
-                    if ((smask >> m) & 1u) Bs[base + off[m]] = z[m];
+                for (int m = 0; m < 8; ++m) sbr_st_if(&Bs[base + off[m]], z[m], (smask >> m) & 1u);
             }
             if (lane < 8 && lo + lane < N) Q2[(size_t)s * N + (lo - s - 1) + lane] = (lane == 0) ? tau : ur * scale;
             __syncwarp();
-            __threadfence_block();
+            sbr_fence_cta();
             if (lane == 0) prog[u] = s * 256 + k + 1;
         }
         __syncwarp();
