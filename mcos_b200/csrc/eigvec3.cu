@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) yr[m] *= sc;
     // y <- H_0 ... H_{N-2-off} y ; reflector k: u[k+off] = 1, u[j] = A[k][j] for j > k+off
-    // (off = 1: one-stage tridiagonalisation; off = 8: panel reflectors of sy2sb_kernel)
+    // (off = 1: one-stage tridiagonalisation; off = 8: panel reflectors of sy2sb_kernel).  (A register double buffer that
+    // prefetches the next reflector row was slower: 164 registers instead of ~100 cost more in occupancy than it hid.)
     for (int k = N - 2 - off; k >= 0; --k) {
         const double tk = tau[k];
         if (tk == 0.0) continue;
@@ -260,6 +261,7 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
     if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else if (N <= 768) backtransform_kernel<24><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     const size_t smem = (2 * n + EV3_VMAX + EV3_VMAX * n) * sizeof(double);
@@ -349,6 +351,7 @@ int mcosb_dev_detone(mcosb_ctx* ctx, int S, double* dcov, int n_remove, int* dst
     if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
     else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
     else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else if (N <= 768) backtransform_kernel<24><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
     else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     detone_kernel<<<dim3((N + 7) / 8, S), 256, n * sizeof(double), ctx->stream>>>(V, lam, n_remove, sigma, N, dcov);

@@ -244,9 +244,25 @@ __global__ void __launch_bounds__(Q2B_NT) q2back_kernel(const double* __restrict
         Y[idx] = (i < N && vec < nf) ? y[(size_t)i * G + vec] : 0.0;
     }
     __syncthreads();
+    // the reflectors of sweep s (N - 1 - s doubles) are staged in shared memory one sweep ahead: the global load of the
+    // next row overlaps the work on the current one
+    double* Qs = Y + (size_t)(N + 8) * Q2B_V;      // [2][N + 8]
+    constexpr int PF = 3;                          // N <= 768
+    for (int idx = tid; idx < 2 * (N + 8); idx += Q2B_NT) Qs[idx] = 0.0;
+    __syncthreads();
+    if (N >= 3)
+        for (int idx = tid; idx < 2; idx += Q2B_NT) Qs[idx] = Q2[(size_t)(N - 3) * N + idx];   // sweep N-3: rows N-2, N-1
+    __syncthreads();
     for (int s = N - 3; s >= 0; --s) {
         const int nk = (N - 3 - s) / 8 + 1;
-        const double* q = Q2 + (size_t)s * N;
+        const int cur = (N - 3 - s) & 1;
+        const double* q = Qs + (size_t)cur * (N + 8);
+        double pf[PF];
+#pragma unroll
+        for (int r = 0; r < PF; ++r) {
+            const int idx = tid + Q2B_NT * r;
+            pf[r] = (s > 0 && idx < N - s) ? Q2[(size_t)(s - 1) * N + idx] : 0.0;
+        }
         for (int item = tid; item < nk * Q2B_V; item += Q2B_NT) {
             const int k = item >> 4, vec = item & 15;
             if (vec < nf) {
@@ -267,6 +283,12 @@ __global__ void __launch_bounds__(Q2B_NT) q2back_kernel(const double* __restrict
                 for (int m = 0; m < 8; ++m) Y[(lo + m) * Q2B_V + vec] = fma(-dot, v[m], yy[m]);
             }
         }
+        double* qn = Qs + (size_t)(cur ^ 1) * (N + 8);
+#pragma unroll
+        for (int r = 0; r < PF; ++r) {
+            const int idx = tid + Q2B_NT * r;
+            if (s > 0 && idx < N - s) qn[idx] = pf[r];
+        }
         __syncthreads();
     }
     for (int idx = tid; idx < N * Q2B_V; idx += Q2B_NT) {
@@ -277,7 +299,7 @@ __global__ void __launch_bounds__(Q2B_NT) q2back_kernel(const double* __restrict
 
 int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, double* Wy) {
     const int N = ctx->N;
-    const size_t smem = (size_t)(N + 8) * Q2B_V * sizeof(double);
+    const size_t smem = ((size_t)(N + 8) * Q2B_V + 2 * (size_t)(N + 8)) * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(q2back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     q2back_kernel<<<S, Q2B_NT, smem, ctx->stream>>>(Q2, nf, N, S, Wy);
     MCOSB_LAUNCHED(ctx, MK_Q2BACK);
