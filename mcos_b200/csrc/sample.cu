@@ -67,7 +67,11 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
     const int J = blockIdx.x;
     const size_t m0 = (size_t)blockIdx.y * DM_BM;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
+    // column quarter of the warp: the two warps of a scheduler (wid and wid + 4) take quarters q and 3 - q, so that the
+    // k-slabs a warp may skip inside the diagonal block of L (those entirely above its columns: 6, 4, 2, 0 of 8 for
+    // quarters 0..3) take the same load off every scheduler
+    const int cq = (wid >> 2) ? 3 - (wid & 3) : (wid & 3);
+    const int wm0 = (wid >> 2) * DM_WM, wn0 = cq * DM_WN;
     const int lk = tid % DM_BK, lr = tid / DM_BK;  // loader: k fixed, row = lr + 16 r
 
     double acc[DM_MB][DM_NB][2];
@@ -104,7 +108,8 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
         if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
         cp_async_commit();
         const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_MMAJOR;
-        dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc);
+        if (kt * DM_BK <= J * DM_BN + wn0 + DM_WN - 1)   // L[j][k] = 0 for k > j: nothing for this warp's columns
+            dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc);
     }
     const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
