@@ -297,11 +297,25 @@ __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __res
     const double pad = 2.2e-16 * span * (2.0 * N) + 1e-300;
     lo -= pad;
     hi += pad;
+    // one multisection step shared by the whole matrix: Sturm counts on a uniform grid of N points (one per thread and
+    // round) give every eigenvalue a bracket of width span / N for one evaluation instead of log2(N) bisection steps
+    int* cnts = reinterpret_cast<int*>(sde + N);   // [N] number of eigenvalues below grid point i + 1
+    __syncthreads();
+    const double h = (hi - lo) / (double)N;
+    for (int i = tid; i < N; i += EV_THREADS) cnts[i] = sturm_count(sde, N, fma(h, (double)(i + 1), lo));
+    __syncthreads();
+    // below ~4 ulp of the spectrum's scale the tridiagonal form itself is not accurate; stop there
+    const double tol = 8.9e-16 * fmax(span, 1e-300);
     for (int j = tid; j < N; j += EV_THREADS) {  // j-th smallest eigenvalue
-        double a = lo, b = hi;
+        int l0 = 0, l1 = N - 1;                  // smallest i with cnts[i] > j (cnts[N-1] = N)
+        while (l0 < l1) {
+            const int mid = (l0 + l1) >> 1;
+            if (cnts[mid] > j) l1 = mid; else l0 = mid + 1;
+        }
+        double a = fma(h, (double)l0, lo), b = fma(h, (double)(l0 + 1), lo);
         for (int it = 0; it < 200; ++it) {
             double mid = 0.5 * (a + b);
-            if (!(mid > a && mid < b)) break;
+            if (!(mid > a && mid < b) || b - a <= tol) break;
             int c = sturm_count(sde, N, mid);
             if (c > j) b = mid; else a = mid;
         }
@@ -853,7 +867,7 @@ int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, 
     corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
     MCOSB_LAUNCHED(ctx, MK_CORR);
     MCOSB_TRY(mcosb_dev_tridiagonalize(ctx, S, A, d, e, tau, q2));
-    size_t smem_ev = 2 * n * sizeof(double);
+    size_t smem_ev = 2 * n * sizeof(double) + n * sizeof(int);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ev));
     eigvals_kernel<<<S, EV_THREADS, smem_ev, ctx->stream>>>(d, e, N, lam);
     MCOSB_LAUNCHED(ctx, MK_EIGVALS);
