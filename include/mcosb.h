@@ -89,7 +89,7 @@ int mcosb_denoise(mcosb_ctx* ctx, int S, double* cov_inout, int n_obs, double ba
                   int* n_facts, int* status);
 
 /* Selects the tridiagonalisation behind np.linalg.eigh (covariance_transformer.py:105) in mcosb_denoise / mcosb_detone /
- * mcosb_run: 0 = automatic (two-stage for 96 <= n_assets <= 696), 1 = one-stage blocked Householder, 2 = two-stage
+ * mcosb_run: 0 = automatic (two-stage for 128 <= n_assets <= 696), 1 = one-stage blocked Householder, 2 = two-stage
  * (dense -> band on the FP64 tensor cores, band -> tridiagonal by bulge chasing in shared memory). */
 int mcosb_set_eig_method(mcosb_ctx* ctx, int method);
 

@@ -6,7 +6,7 @@
 #include "common.cuh"
 
 #define SBR_B 8
-#define SBR_MIN_N 96   // below this the one-stage kernels are used (mcosb_dev_eig_prepare)
+#define SBR_MIN_N 128   // below this the one-stage kernels are used (mcosb_dev_eig_prepare)
 
 // Each returns 1 if launched, 0 if the problem size is outside its range (nothing launched), < 0 on error.
 int mcosb_launch_sy2sb(mcosb_ctx* ctx, int S, double* A, double* tau);
