@@ -106,68 +106,94 @@ __global__ void __launch_bounds__(64) inviter_kernel(const double* __restrict__ 
     // the last sweep's overall scale is irrelevant: backtransform_kernel normalises
 }
 
-// One warp per (simulation, eigenvector). MAXM = ceil(N / 32) register slots per lane.
+// One warp per (simulation, eigenvector), MAXM = ceil(N / 32) register slots per lane; a CTA holds 8 vectors of ONE
+// simulation (two CTAs per simulation), so the reflector rows are staged in shared memory once per CTA, one reflector
+// ahead of the one being applied (every warp used to read its own copy from L2 with the latency exposed at each step).
 template <int MAXM>
 __global__ void __launch_bounds__(256) backtransform_kernel(const double* __restrict__ Aall,
                                                             const double* __restrict__ tauall,
                                                             const int* __restrict__ nfall, int N, int S,
                                                             const double* __restrict__ W, double* __restrict__ V,
                                                             int* __restrict__ status, int off) {
+    extern __shared__ double rowbuf[];           // [2][N]
+    constexpr int PFN = (MAXM * 32 + 255) / 256;
     const size_t G = (size_t)S * EV3_VMAX;
-    const size_t g = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (g >= G) return;
-    const int sim = (int)(g / EV3_VMAX), vec = (int)(g % EV3_VMAX);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int sim = blockIdx.x / (EV3_VMAX / 8), vec = (blockIdx.x % (EV3_VMAX / 8)) * 8 + wid;
+    const size_t g = (size_t)sim * EV3_VMAX + vec;
     const int nf = nfall[sim];
-    if (nf > EV3_VMAX || vec >= nf) return;
+    if (nf > EV3_VMAX || (vec - wid) >= nf) return;      // nothing for this CTA (uniform)
+    const bool active = vec < nf;
     const double* A = Aall + (size_t)sim * N * N;
     const double* tau = tauall + (size_t)sim * N;
     const double* y = W + 4 * (size_t)N * G + g;
     double yr[MAXM];
-    double mx = 0.0;
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m) {
-        const int i = lane + 32 * m;
-        yr[m] = (i < N) ? y[(size_t)i * G] : 0.0;
-        mx = fmax(mx, fabs(yr[m]));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const double pre = 1.0 / mx;
-    double nrm = 0.0;
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m) { yr[m] *= pre; nrm = fma(yr[m], yr[m], nrm); }
-    nrm = warp_sum(nrm);
-    const double sc = 1.0 / sqrt(nrm);
-    if (!isfinite(sc) || !isfinite(pre)) {
-        if (lane == 0 && status) atomicOr(&status[sim], MCOSB_ST_EIGVEC);
-    }
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m) yr[m] *= sc;
-    // y <- H_0 ... H_{N-2-off} y ; reflector k: u[k+off] = 1, u[j] = A[k][j] for j > k+off
-    // (off = 1: one-stage tridiagonalisation; off = 8: panel reflectors of sy2sb_kernel).  (A register double buffer that
-    // prefetches the next reflector row was slower: 164 registers instead of ~100 cost more in occupancy than it hid.)
-    for (int k = N - 2 - off; k >= 0; --k) {
-        const double tk = tau[k];
-        if (tk == 0.0) continue;
-        const double* u = A + (size_t)k * N;
-        double ur[MAXM];
-        double dot = 0.0;
+    if (active) {
+        double mx = 0.0;
 #pragma unroll
         for (int m = 0; m < MAXM; ++m) {
-            const int j = lane + 32 * m;
-            ur[m] = (j > k + off && j < N) ? u[j] : ((j == k + off) ? 1.0 : 0.0);
-            dot = fma(ur[m], yr[m], dot);
+            const int i = lane + 32 * m;
+            yr[m] = (i < N) ? y[(size_t)i * G] : 0.0;
+            mx = fmax(mx, fabs(yr[m]));
         }
-        dot = warp_sum(dot) * tk;
 #pragma unroll
-        for (int m = 0; m < MAXM; ++m) yr[m] = fma(-dot, ur[m], yr[m]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const double pre = 1.0 / mx;
+        double nrm = 0.0;
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) { yr[m] *= pre; nrm = fma(yr[m], yr[m], nrm); }
+        nrm = warp_sum(nrm);
+        const double sc = 1.0 / sqrt(nrm);
+        if (!isfinite(sc) || !isfinite(pre)) {
+            if (lane == 0 && status) atomicOr(&status[sim], MCOSB_ST_EIGVEC);
+        }
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) yr[m] *= sc;
     }
-    double* out = V + g * (size_t)N;
+    // y <- H_0 ... H_{N-2-off} y ; reflector k: u[k+off] = 1, u[j] = A[k][j] for j > k+off
+    // (off = 1: one-stage tridiagonalisation; off = 8: panel reflectors of sy2sb_kernel)
+    const int K0 = N - 2 - off;
+    if (K0 >= 0)
+        for (int j = tid; j < N; j += 256) rowbuf[j] = (j > K0 + off) ? A[(size_t)K0 * N + j] : 0.0;
+    __syncthreads();
+    for (int k = K0; k >= 0; --k) {
+        const int cur = (K0 - k) & 1;
+        double pf[PFN];
 #pragma unroll
-    for (int m = 0; m < MAXM; ++m) {
-        const int i = lane + 32 * m;
-        if (i < N) out[i] = yr[m];
+        for (int r = 0; r < PFN; ++r) {
+            const int j = tid + 256 * r;
+            pf[r] = (k > 0 && j < N && j > k - 1 + off) ? A[(size_t)(k - 1) * N + j] : 0.0;
+        }
+        const double tk = tau[k];
+        if (active && tk != 0.0) {
+            const double* u = rowbuf + (size_t)cur * N;
+            double ur[MAXM];
+            double dp[4] = {0.0, 0.0, 0.0, 0.0};     // four chains: a dependent FP64 FMA costs ~25 cycles
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                const int j = lane + 32 * m;
+                ur[m] = (j > k + off && j < N) ? u[j] : ((j == k + off) ? 1.0 : 0.0);
+                dp[m & 3] = fma(ur[m], yr[m], dp[m & 3]);
+            }
+            double dot = warp_sum((dp[0] + dp[1]) + (dp[2] + dp[3])) * tk;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) yr[m] = fma(-dot, ur[m], yr[m]);
+        }
+        double* nb = rowbuf + (size_t)(cur ^ 1) * N;
+#pragma unroll
+        for (int r = 0; r < PFN; ++r) {
+            const int j = tid + 256 * r;
+            if (j < N) nb[j] = pf[r];
+        }
+        __syncthreads();
+    }
+    if (active) {
+        double* out = V + g * (size_t)N;
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            const int i = lane + 32 * m;
+            if (i < N) out[i] = yr[m];
+        }
     }
 }
 
@@ -258,11 +284,11 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
     const int off = Q2 ? SBR_B : 1;
     if (Q2) MCOSB_TRY(mcosb_launch_q2back(ctx, S, Q2, nf, W + 4 * n * G) == 1 ? MCOSB_OK : MCOSB_ERR_STATE);
     const unsigned bt_grid = (unsigned)((G + 7) / 8);
-    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
-    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
-    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
-    else if (N <= 768) backtransform_kernel<24><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
-    else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else if (N <= 768) backtransform_kernel<24><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    else backtransform_kernel<32><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     const size_t smem = (2 * n + EV3_VMAX + EV3_VMAX * n) * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -348,11 +374,11 @@ int mcosb_dev_detone(mcosb_ctx* ctx, int S, double* dcov, int n_remove, int* dst
     MCOSB_LAUNCHED(ctx, MK_INVITER);
     if (Q2) MCOSB_TRY(mcosb_launch_q2back(ctx, S, Q2, nf, W + 4 * n * G) == 1 ? MCOSB_OK : MCOSB_ERR_STATE);
     const unsigned bt_grid = (unsigned)((G + 7) / 8);
-    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
-    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
-    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
-    else if (N <= 768) backtransform_kernel<24><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
-    else backtransform_kernel<32><<<bt_grid, 256, 0, ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else if (N <= 768) backtransform_kernel<24><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
+    else backtransform_kernel<32><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, dstatus, off);
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     detone_kernel<<<dim3((N + 7) / 8, S), 256, n * sizeof(double), ctx->stream>>>(V, lam, n_remove, sigma, N, dcov);
     MCOSB_LAUNCHED(ctx, MK_DETONE);
