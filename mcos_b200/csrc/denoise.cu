@@ -277,9 +277,11 @@ __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __res
     const double* d = dall + (size_t)s * N;
     const double* e = eall + (size_t)s * N;
     double lo = 1e300, hi = -1e300;
+    int bad = 0;
     for (int i = tid; i < N; i += EV_THREADS) {
         double di = d[i], ei = (i < N - 1) ? e[i] : 0.0, em = (i > 0) ? e[i - 1] : 0.0;
         sde[i] = make_double2(di, em * em);
+        bad |= !(isfinite(di) && isfinite(ei));
         double r = fabs(ei) + fabs(em);
         lo = fmin(lo, di - r);
         hi = fmax(hi, di + r);
@@ -290,7 +292,10 @@ __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __res
         hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     if ((tid & 31) == 0) { red_lo[tid >> 5] = lo; red_hi[tid >> 5] = hi; }
-    __syncthreads();
+    if (__syncthreads_or(bad)) {   // a non-finite tridiagonal (NaN in the input): NaN eigenvalues, flagged downstream
+        for (int j = tid; j < N; j += EV_THREADS) lamall[(size_t)s * N + j] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
     lo = red_lo[0]; hi = red_hi[0];
     for (int i = 1; i < EV_THREADS / 32; ++i) { lo = fmin(lo, red_lo[i]); hi = fmax(hi, red_hi[i]); }
     const double span = fmax(fabs(lo), fabs(hi));

@@ -97,3 +97,28 @@ def test_detone_two_stage():
     eng.set_eig_method(2)
     o2, _ = eng.detone(a, 2)
     assert_allclose(o2, o1, rtol=1e-8, atol=1e-12)
+
+
+def test_rank_deficient_and_nan_inputs_on_the_two_stage_path():
+    """T < N (hundreds of exactly repeated zero eigenvalues) and a NaN-poisoned matrix in the same batch: no hang, the clean
+    simulations are untouched, the poisoned one is flagged."""
+    n, t = 160, 40
+    rng = np.random.RandomState(11)
+    covs = np.stack([np.cov(rng.standard_normal((t, n)) * rng.uniform(0.05, 0.2, n), rowvar=False) for _ in range(4)])
+    eng = Engine(n, t)
+    eng.set_eig_method(2)
+    corr = np.stack([c / np.sqrt(np.outer(np.diag(c), np.diag(c))) for c in covs])
+    d, e = eng.tridiagonalize(corr)
+    for i in range(4):
+        assert_allclose(_tri_eigs(d[i], e[i]), np.linalg.eigvalsh(corr[i]), rtol=0, atol=1e-12 * n)
+    good, info_good = eng.denoise(covs, t)
+    assert (info_good["status"] == 0).all()
+    for i in range(4):
+        ref = oracle.denoise_details(covs[i], t)
+        assert int(info_good["n_facts"][i]) == int(ref["n_facts"])
+        assert_allclose(good[i], ref["cov"], rtol=1e-6, atol=1e-9 * np.abs(ref["cov"]).max())
+    bad = covs.copy()
+    bad[1, 3, 5] = bad[1, 5, 3] = np.nan
+    out, info = eng.denoise(bad, t)
+    assert info["status"][1] != 0 and (info["status"][[0, 2, 3]] == 0).all()
+    assert np.array_equal(out[[0, 2, 3]], good[[0, 2, 3]])
