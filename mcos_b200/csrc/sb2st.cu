@@ -48,7 +48,11 @@ __device__ __forceinline__ void sbr_st_if(double* p, double v, unsigned pred) {
 
 // acquire/release fence at CTA scope: orders the band updates against the progress flag (the sequentially consistent
 // __threadfence_block is not needed)
+#ifdef SBR_NO_FENCE
+__device__ __forceinline__ void sbr_fence_cta() { asm volatile("" ::: "memory"); }
+#else
 __device__ __forceinline__ void sbr_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+#endif
 
 template <int W>
 __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict__ Aall, int N, double* __restrict__ dall,
@@ -199,6 +203,202 @@ __global__ void __launch_bounds__(W * 32) sb2st_kernel(const double* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same chase with the reflector applied as tiny GEMMs on the FP64 tensor core: H = I - gam u u' is formed explicitly in
+// fragment layout (each lane needs five entries of u) and a step is 8 DMMA.8x8x4:
+//   C_k' = H C_k (2),  T = H D_k, D_k' = T H (2 + 2; the C fragment of T is reused as A operand with the k index permuted),
+//   C_{k+1}' = C_{k+1} H (2; H is symmetric, so its A fragments double as B fragments).
+// No dot products, no reductions: the step shrinks from ~480 to ~190 instructions and its dependent chain from ~50 FP64
+// operations to the Householder scalars plus two DMMA latencies (step 1030 cycles instead of 1350 for a lone warp).  But
+// the explicit 8 x 8 x 8 products cost 128 FP64-pipe cycles per step against ~130 for ALL the FP64 work of the rank-1
+// form, so with 24 warps per SM this kernel is FP64-pipe-bound where the other is issue-bound: 7.2 us per 500 x 500 matrix
+// either way.  Kept selectable (MCOSB_SB2ST_MMA=1) and tested; same storage, pipeline protocol and Q2 layout as above;
+// the follower sleeps on an mbarrier instead of polling.
+// ---------------------------------------------------------------------------------------------------------------
+#include "dmma.cuh"
+#define SBR_MBARS 100   // >= steps per sweep + 2 (N <= 768: 96 steps)
+
+// mbarrier helpers: the follower of a sweep sleeps in hardware (try_wait) instead of polling shared memory -- polling
+// warps flood the shared-memory / shuffle pipe the working warp of the same SM sub-partition needs
+__device__ __forceinline__ void sbr_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void sbr_mbar_arrive(unsigned long long* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared.b64 st, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void sbr_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "W_%=: mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+        "@!p bra W_%=;\n }" ::"r"(a), "r"(parity) : "memory");
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32) sb2st_mma_kernel(const double* __restrict__ Aall, int N, double* __restrict__ dall,
+                                                           double* __restrict__ eall, double* __restrict__ Q2all) {
+    extern __shared__ double Bs[];                 // [(N + 16) * 16]
+    __shared__ volatile int prog[W];
+    __shared__ unsigned long long mbar[W][SBR_MBARS];   // mbar[u][j]: warp u has finished step j of its current sweep
+    const int sim = blockIdx.x;
+    const double* A = Aall + (size_t)sim * N * N;
+    double* Q2 = Q2all + (size_t)sim * N * N;
+    const int tid = threadIdx.x, lane = tid & 31, u = tid >> 5;
+    constexpr int NT = W * 32;
+
+    for (int i = tid; i < (N + 16) * 16; i += NT) Bs[i] = 0.0;
+    if (tid < W) prog[tid] = -1;
+    for (int i = tid; i < W * SBR_MBARS; i += NT) sbr_mbar_init(&mbar[0][0] + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    for (int i = tid; i < N; i += NT) {
+        const double* row = A + (size_t)i * N;
+        for (int d = 0; d <= SBR_B && d <= i; ++d) Bs[(i - d) * 16 + d] = row[i - d];
+    }
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    // element (row lo + r, column lo + c) of the band sits at lo * 16 + c * 16 + (r - c); fixed per-lane offsets:
+    const int oCkL = (g - 8) * 16 + 8 + t - g;                 // C_k[t][g]            (+4: row 4 + t)
+    const int oCkS = (2 * t - 8) * 16 + 8 + g - 2 * t;         // C_k'[g][2t]          (+15: column 2t + 1)
+    auto offD = [](int r, int c) { return r >= c ? c * 16 + r - c : r * 16 + c - r; };
+    const int oDL0 = offD(t, g), oDL1 = offD(4 + t, g);        // D[t][g], D[4+t][g] (symmetric, lower stored)
+    const int oDS = 2 * t * 16 + g - 2 * t;                    // D'[g][2t]            (+15: column 2t + 1)
+    const int oEL = t * 16 + 8 + g - t;                        // E[g][t]              (+60: column 4 + t)
+    const int oES = 2 * t * 16 + 8 + g - 2 * t;                // E'[g][2t]            (+15: column 2t + 1)
+    const unsigned stD0 = 2 * t <= g, stD1 = 2 * t + 1 <= g;
+    const double dA0 = (g == t) ? 1.0 : 0.0, dA1 = (g == 4 + t) ? 1.0 : 0.0;
+    const double dB0 = (2 * t == g) ? 1.0 : 0.0, dB1 = (2 * t + 1 == g) ? 1.0 : 0.0;
+    const int pu = (u + W - 1) % W;
+    int seen = -1;
+#ifdef SB_TIMING
+    long long tw = 0, tc = 0, tmark = clock64();
+    int nsteps = 0;
+#endif
+
+    for (int s = u; s + 2 < N; s += W) {
+        double xsrc = 0.0;                        // E'[g][0] of the previous step (lanes with t == 0): the next x
+        for (int k = 0;; ++k) {
+            const int lo = s + 1 + 8 * k;
+            if (N - lo < 2) break;
+            if (s > 0) {
+                int need_done = k + 3;
+                if (need_done > 255) need_done = 255;
+                const int need = (s - 1) * 256 + need_done;
+                if (seen < need) {
+                    if (lane == 0) {
+                        int cur = prog[pu];
+                        if (cur < need) {          // not there yet: sleep on the barrier of the step we depend on
+                            sbr_mbar_wait(&mbar[pu][min(k + 2, SBR_MBARS - 1)], ((s - 1) / W) & 1);
+                            cur = prog[pu];
+                        }
+                        seen = cur;
+                    }
+                    seen = __shfl_sync(0xffffffffu, seen, 0);
+                    sbr_fence_cta();
+                }
+            }
+#ifdef SB_TIMING
+            { long long n0 = clock64(); tw += n0 - tmark; tmark = n0; }
+#endif
+            const int base = lo * 16;
+            const bool first = (k == 0);
+            // operands of the three blocks (C_k does not exist in step 0: valid memory is read and ignored)
+            const int cb = first ? base + 128 : base;
+            const double ck0 = Bs[cb + oCkL], ck1 = Bs[cb + oCkL + 4];
+            const double d0 = Bs[base + oDL0], d1 = Bs[base + oDL1];
+            const double e0 = Bs[base + oEL], e1 = Bs[base + oEL + 60];
+            double x[8], ug, ut, ut4, u2t, u2t1, xq;
+            if (first) {
+                const double* col = Bs + base - 15;           // column s below the diagonal
+#pragma unroll
+                for (int m = 0; m < 8; ++m) x[m] = col[m];
+                ug = col[g]; ut = col[t]; ut4 = col[4 + t]; u2t = col[2 * t]; u2t1 = col[2 * t + 1];
+                xq = col[lane & 7];
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) x[m] = __shfl_sync(0xffffffffu, xsrc, 4 * m);
+                ug = __shfl_sync(0xffffffffu, xsrc, 4 * g);
+                ut = __shfl_sync(0xffffffffu, xsrc, 4 * t);
+                ut4 = __shfl_sync(0xffffffffu, xsrc, 16 + 4 * t);
+                u2t = __shfl_sync(0xffffffffu, xsrc, 8 * t);
+                u2t1 = __shfl_sync(0xffffffffu, xsrc, 8 * t + 4);
+                xq = __shfl_sync(0xffffffffu, xsrc, 4 * (lane & 7));
+            }
+            const double ss = (x[1] * x[1] + x[2] * x[2]) + (x[3] * x[3] + x[4] * x[4]) +
+                              ((x[5] * x[5] + x[6] * x[6]) + x[7] * x[7]);
+            const double alpha = x[0];
+            double gam = 0.0, tau = 0.0, scale = 0.0, beta = alpha, u0 = 0.0;
+            if (ss > 1e-280) {
+                const double n2 = fma(alpha, alpha, ss);
+                const double rs = sbr_rsqrt(n2);
+                const double tt = fma(fabs(alpha), rs, 1.0);
+                const double rt = sbr_rcp(tt);
+                beta = -copysign(n2 * rs, alpha);
+                u0 = alpha - beta;
+                gam = rs * rs * rt;
+                scale = copysign(rs * rt, alpha);
+                tau = tt;
+            }
+            if (g == 0) ug = u0;
+            if (t == 0) { ut = u0; u2t = u0; }
+            // H = I - gam u u' in fragment layout
+            const double gu = gam * ug;
+            const double hA0 = fma(-gu, ut, dA0), hA1 = fma(-gu, ut4, dA1);
+            const double hB0 = fma(-gu, u2t, dB0), hB1 = fma(-gu, u2t1, dB1);
+            double c0 = 0.0, c1 = 0.0, t0 = 0.0, t1 = 0.0, ee0 = 0.0, ee1 = 0.0, dd0 = 0.0, dd1 = 0.0;
+            dmma_884(ee0, ee1, e0, hA0);               // E' = E H   (critical: its first column is the next x)
+            dmma_884(t0, t1, hA0, d0);                 // T  = H D
+            dmma_884(c0, c1, hA0, ck0);                // C' = H C
+            dmma_884(ee0, ee1, e1, hA1);
+            dmma_884(t0, t1, hA1, d1);
+            dmma_884(c0, c1, hA1, ck1);
+            dmma_884(dd0, dd1, t0, hB0);               // D' = T H   (k index permuted: even / odd columns of T)
+            dmma_884(dd0, dd1, t1, hB1);
+            xsrc = ee0;
+            if (first) {
+                if (lane < 8) Bs[base - 15 + lane] = (lane == 0) ? beta : 0.0;     // column s: (beta, 0, ..., 0)
+            } else {
+                if (t == 0) c0 = (g == 0) ? beta : 0.0;                             // first column of C_k: annihilated
+                Bs[base + oCkS] = c0;
+                Bs[base + oCkS + 15] = c1;
+            }
+            sbr_st_if(&Bs[base + oDS], dd0, stD0);
+            sbr_st_if(&Bs[base + oDS + 15], dd1, stD1);
+            Bs[base + oES] = ee0;
+            Bs[base + oES + 15] = ee1;
+            if (lane < 8 && lo + lane < N) Q2[(size_t)s * N + (lo - s - 1) + lane] = (lane == 0) ? tau : xq * scale;
+            __syncwarp();
+            sbr_fence_cta();
+            if (lane == 0) {
+                prog[u] = s * 256 + k + 1;
+                sbr_mbar_arrive(&mbar[u][k]);
+            }
+#ifdef SB_TIMING
+            { long long n0 = clock64(); tc += n0 - tmark; tmark = n0; ++nsteps; }
+#endif
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // the follower may wait for up to two steps this sweep does not have
+            const int nst = (N - 2 - s + 7) / 8;   // steps of sweep s: lo = s + 1 + 8 k <= N - 2
+            prog[u] = s * 256 + 255;
+            sbr_mbar_arrive(&mbar[u][min(nst, SBR_MBARS - 1)]);
+            sbr_mbar_arrive(&mbar[u][min(nst + 1, SBR_MBARS - 1)]);
+        }
+    }
+#ifdef SB_TIMING
+    if (blockIdx.x == 0 && lane == 0) printf("sb2st warp %d: steps %d wait %lld compute %lld (per step %lld / %lld)\n", u, nsteps, tw, tc, tw / max(nsteps, 1), tc / max(nsteps, 1));
+#endif
+    __syncthreads();
+    double* d = dall + (size_t)sim * N;
+    double* e = eall + (size_t)sim * N;
+    for (int i = tid; i < N; i += NT) {
+        d[i] = Bs[i * 16];
+        e[i] = (i + 1 < N) ? Bs[i * 16 + 1] : 0.0;
+    }
+}
+
 int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double* e, double* Q2) {
     const int N = ctx->N;
     const size_t smem = (size_t)(N + 16) * 16 * sizeof(double);
@@ -213,11 +413,27 @@ int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         sb2st_kernel<W><<<S, W * 32, smem, ctx->stream>>>(A, N, d, e, Q2);                                            \
     } while (0)
-    if (Wsel == 1) SB2ST_LAUNCH(1);
+    static int mma = -1;
+    if (mma < 0) {
+        const char* e2 = getenv("MCOSB_SB2ST_MMA");
+        mma = e2 ? atoi(e2) : 0;   // measured: 7.2 us per 500 x 500 matrix either way (profiles/sbr_kernels_r01c.md)
+    }
+#define SB2ST_LAUNCH_MMA(W)                                                                                           \
+    do {                                                                                                              \
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(sb2st_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        sb2st_mma_kernel<W><<<S, W * 32, smem, ctx->stream>>>(A, N, d, e, Q2);                                        \
+    } while (0)
+    if (mma) {
+        if (Wsel == 1) SB2ST_LAUNCH_MMA(1);
+        else if (Wsel == 2) SB2ST_LAUNCH_MMA(2);
+        else if (Wsel == 8) SB2ST_LAUNCH_MMA(8);
+        else SB2ST_LAUNCH_MMA(4);
+    } else if (Wsel == 1) SB2ST_LAUNCH(1);
     else if (Wsel == 2) SB2ST_LAUNCH(2);
     else if (Wsel == 8) SB2ST_LAUNCH(8);
     else SB2ST_LAUNCH(4);
 #undef SB2ST_LAUNCH
+#undef SB2ST_LAUNCH_MMA
     MCOSB_LAUNCHED(ctx, MK_SB2ST);
     return 1;
 }

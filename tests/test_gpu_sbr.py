@@ -122,3 +122,26 @@ def test_rank_deficient_and_nan_inputs_on_the_two_stage_path():
     out, info = eng.denoise(bad, t)
     assert info["status"][1] != 0 and (info["status"][[0, 2, 3]] == 0).all()
     assert np.array_equal(out[[0, 2, 3]], good[[0, 2, 3]])
+
+
+def test_tensor_core_bulge_chasing_variant():
+    """sb2st_mma_kernel (MCOSB_SB2ST_MMA=1): the reflectors applied as 8 x 8 GEMMs on the FP64 tensor core."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import numpy as np
+        from mcos_b200.engine import Engine
+        n = 300
+        rng = np.random.RandomState(4)
+        a = np.stack([np.corrcoef(rng.standard_normal((2 * n, n)), rowvar=False) for _ in range(3)])
+        eng = Engine(n, 2 * n)
+        eng.set_eig_method(2)
+        d, e = eng.tridiagonalize(a)
+        for i in range(3):
+            t = np.diag(d[i]) + np.diag(e[i][:n - 1], 1) + np.diag(e[i][:n - 1], -1)
+            err = np.abs(np.linalg.eigvalsh(t) - np.linalg.eigvalsh(a[i])).max()
+            assert err < 1e-12 * n, err
+        print("ok")
+    """)
+    env = dict(os.environ, MCOSB_SB2ST_MMA="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
