@@ -64,9 +64,17 @@ __device__ __forceinline__ double nc_block_sum(double v, NcSm& s) { return block
 __device__ void nc_dist_to_point(const double* __restrict__ X, const double* __restrict__ cm, int N, int c, NcSm& s,
                                  double* out) {
     for (int i = threadIdx.x; i < N; i += NC_THREADS) {
-        double dot = 0.0;
-        for (int d = 0; d < N; ++d)
-            dot = fma(X[(size_t)d * N + i] - cm[d], X[(size_t)d * N + c] - cm[d], dot);  // X symmetric: column = row
+        // four independent chains: a dependent FP64 FMA costs ~25 cycles on B200 and only N threads of the CTA work here
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        int d = 0;
+        for (; d + 3 < N; d += 4) {
+            d0 = fma(X[(size_t)d * N + i] - cm[d], X[(size_t)d * N + c] - cm[d], d0);  // X symmetric: column = row
+            d1 = fma(X[(size_t)(d + 1) * N + i] - cm[d + 1], X[(size_t)(d + 1) * N + c] - cm[d + 1], d1);
+            d2 = fma(X[(size_t)(d + 2) * N + i] - cm[d + 2], X[(size_t)(d + 2) * N + c] - cm[d + 2], d2);
+            d3 = fma(X[(size_t)(d + 3) * N + i] - cm[d + 3], X[(size_t)(d + 3) * N + c] - cm[d + 3], d3);
+        }
+        for (; d < N; ++d) d0 = fma(X[(size_t)d * N + i] - cm[d], X[(size_t)d * N + c] - cm[d], d0);
+        const double dot = (d0 + d1) + (d2 + d3);
         double v = s.xnorm[i] - 2.0 * dot + s.xnorm[c];
         if (i == c) v = 0.0;
         out[i] = v > 0.0 ? v : 0.0;
@@ -82,13 +90,29 @@ __device__ void nc_assign(const double* __restrict__ X, int N, int k, NcSm& s) {
         s.cn2[j] = q;
     }
     __syncthreads();
+    // one thread per (point, centre) pair (only N of the CTA's threads would work with one thread per point); the scores
+    // go through s.cnew (free during the E-step), then each point takes the argmin, lowest j on ties
+    double* score = s.cnew;
+    for (int p = threadIdx.x; p < N * k; p += NC_THREADS) {
+        const int i = p % N, j = p / N;
+        const double* ca = s.centers + j * N;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int d = 0;
+        for (; d + 3 < N; d += 4) {
+            a0 = fma(X[(size_t)d * N + i] - s.colmean[d], ca[d], a0);
+            a1 = fma(X[(size_t)(d + 1) * N + i] - s.colmean[d + 1], ca[d + 1], a1);
+            a2 = fma(X[(size_t)(d + 2) * N + i] - s.colmean[d + 2], ca[d + 2], a2);
+            a3 = fma(X[(size_t)(d + 3) * N + i] - s.colmean[d + 3], ca[d + 3], a3);
+        }
+        for (; d < N; ++d) a0 = fma(X[(size_t)d * N + i] - s.colmean[d], ca[d], a0);
+        score[p] = s.cn2[j] - 2.0 * ((a0 + a1) + (a2 + a3));
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < N; i += NC_THREADS) {
         double bestv = INFINITY;
         int bestj = 0;
         for (int j = 0; j < k; ++j) {
-            double dot = 0.0;
-            for (int d = 0; d < N; ++d) dot = fma(X[(size_t)d * N + i] - s.colmean[d], s.centers[j * N + d], dot);
-            double v = s.cn2[j] - 2.0 * dot;
+            const double v = score[j * N + i];
             if (v < bestv) { bestv = v; bestj = j; }
         }
         s.labels[i] = bestj;
@@ -201,10 +225,17 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
             __syncthreads();
             for (int idx = tid; idx < k * N; idx += NC_THREADS) {
                 const int j = idx / N, d = idx % N;
-                double acc = 0.0;
-                for (int i = 0; i < N; ++i)
-                    if (s.labels[i] == j) acc += X[(size_t)i * N + d] - s.colmean[d];
-                s.cnew[idx] = acc;
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+                const double cmd = s.colmean[d];
+                int i = 0;
+                for (; i + 3 < N; i += 4) {
+                    c0 += (s.labels[i] == j) ? X[(size_t)i * N + d] - cmd : 0.0;
+                    c1 += (s.labels[i + 1] == j) ? X[(size_t)(i + 1) * N + d] - cmd : 0.0;
+                    c2 += (s.labels[i + 2] == j) ? X[(size_t)(i + 2) * N + d] - cmd : 0.0;
+                    c3 += (s.labels[i + 3] == j) ? X[(size_t)(i + 3) * N + d] - cmd : 0.0;
+                }
+                for (; i < N; ++i) c0 += (s.labels[i] == j) ? X[(size_t)i * N + d] - cmd : 0.0;
+                s.cnew[idx] = (c0 + c1) + (c2 + c3);
             }
             __syncthreads();
             if (tid == 0) {
