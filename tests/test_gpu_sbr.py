@@ -145,3 +145,20 @@ def test_tensor_core_bulge_chasing_variant():
     env = dict(os.environ, MCOSB_SB2ST_MMA="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_automatic_method_outside_the_two_stage_range():
+    """N = 700 > 696 (shared memory of stage 1): automatic selection falls back to the one-stage kernel, forcing the
+    two-stage method is an argument error -- never a silent wrong answer."""
+    from mcos_b200._lib import MCOSBError
+    n = 700
+    a = _corr_batch(n, 2, 3)
+    eng = Engine(n, 2 * n)
+    d, e = eng.tridiagonalize(a)
+    for i in range(2):
+        assert_allclose(_tri_eigs(d[i], e[i]), np.linalg.eigvalsh(a[i]), rtol=0, atol=2e-13 * n)
+    eng.set_eig_method(2)
+    with pytest.raises(MCOSBError):
+        eng.tridiagonalize(a)
+    with pytest.raises(MCOSBError):
+        eng.set_eig_method(3)
