@@ -44,9 +44,10 @@ void mcosb_launch_euclid(mcosb_ctx* ctx, int S, const double* D, double* E);
 struct NcSm {
     double* centers;   // [kmax][N]
     double* cnew;      // [kmax][N]   (aliased by the silhouette per-cluster distance sums [kmax][N])
-    double* xnorm;     // [N]  squared norms of the centred points
+    double* xnorm;     // [N]  (k-means++: distances to the best candidate so far)
     double* closest;   // [N]  k-means++ closest squared distance / generic per-point scratch
-    double* cand;      // [N]  per-point scratch
+    double* cand;      // [NC_CG][N]  candidate distances (k-means++) / per-point scratch
+    double* bestd;     // [N]  distances to the best candidate so far
     double* colmean;   // [N]
     double* cn2;       // [kmax] squared norms of centres
     double* shift;     // [kmax]
@@ -56,30 +57,93 @@ struct NcSm {
     int* lbest;        // [N]
     int* counts;       // [kmax]
     int* ired;         // [32]
+    int* picks;        // [NC_CG] candidate ids of the current k-means++ group
+    int* members;      // [N] point ids grouped by cluster (ascending inside a cluster)
+    int* cstart;       // [kmax + 1]
 };
 
 __device__ __forceinline__ double nc_block_sum(double v, NcSm& s) { return block_sum(v, s.red); }
 
-// squared distance of every point to point `c` via sklearn's identity ||x||^2 - 2 x.y + ||y||^2 (clamped at 0); out[i]
-__device__ void nc_dist_to_point(const double* __restrict__ X, const double* __restrict__ cm, int N, int c, NcSm& s,
-                                 double* out) {
+// squared distance of every point to point `c`: the Euclidean distances between the rows of D are already there for the
+// silhouettes (E, hrp_euclid_kernel), and centring does not change a difference, so ||x_i - x_c||^2 = E[c][i]^2 -- one
+// coalesced row read instead of an N-term dot product per point (sklearn evaluates ||x||^2 - 2 x.y + ||y||^2, which agrees
+// to rounding; the clustering is "not bit for bit" anyway, see the header).
+__device__ void nc_dist_to_point(const double* __restrict__ E, int N, int c, double* out) {
     for (int i = threadIdx.x; i < N; i += NC_THREADS) {
-        // four independent chains: a dependent FP64 FMA costs ~25 cycles on B200 and only N threads of the CTA work here
-        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-        int d = 0;
-        for (; d + 3 < N; d += 4) {
-            d0 = fma(X[(size_t)d * N + i] - cm[d], X[(size_t)d * N + c] - cm[d], d0);  // X symmetric: column = row
-            d1 = fma(X[(size_t)(d + 1) * N + i] - cm[d + 1], X[(size_t)(d + 1) * N + c] - cm[d + 1], d1);
-            d2 = fma(X[(size_t)(d + 2) * N + i] - cm[d + 2], X[(size_t)(d + 2) * N + c] - cm[d + 2], d2);
-            d3 = fma(X[(size_t)(d + 3) * N + i] - cm[d + 3], X[(size_t)(d + 3) * N + c] - cm[d + 3], d3);
-        }
-        for (; d < N; ++d) d0 = fma(X[(size_t)d * N + i] - cm[d], X[(size_t)d * N + c] - cm[d], d0);
-        const double dot = (d0 + d1) + (d2 + d3);
-        double v = s.xnorm[i] - 2.0 * dot + s.xnorm[c];
-        if (i == c) v = 0.0;
-        out[i] = v > 0.0 ? v : 0.0;
+        const double e = E[(size_t)c * N + i];
+        out[i] = e * e;
     }
     __syncthreads();
+}
+
+// k-means++ draws its local trials all at once (candidate_ids = searchsorted(cumsum(closest), rand_vals)); they are
+// handled NC_CG at a time: one parallel prefix scan finds the picks (the serial scan by one thread was 60 % of the kernel),
+// one pass over the points gives the distances to all of them.
+#define NC_CG 4
+
+// picks[t] = smallest i with closest[0] + ... + closest[i] >= vals[t] (N - 1 if none), t < nv.
+__device__ void nc_pick_multi(const double* __restrict__ wgt, int N, const double (&vals)[NC_CG], int nv, NcSm& s) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = (N + NC_THREADS - 1) / NC_THREADS;   // consecutive points per thread
+    const int i0 = tid * chunk;
+    double ls = 0.0;
+    for (int e = 0; e < chunk; ++e)
+        if (i0 + e < N) ls += wgt[i0 + e];
+    double inc = ls;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double tt = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += tt;
+    }
+    __syncthreads();                       // red / picks free
+    if (lane == 31) s.red[wid] = inc;
+    if (tid < NC_CG) s.picks[tid] = N - 1;
+    __syncthreads();
+    double acc = inc - ls;
+    for (int ww = 0; ww < wid; ++ww) acc += s.red[ww];
+    bool done[NC_CG];
+#pragma unroll
+    for (int t = 0; t < NC_CG; ++t) done[t] = t >= nv;
+    for (int e = 0; e < chunk; ++e) {
+        if (i0 + e < N) {
+            acc += wgt[i0 + e];
+#pragma unroll
+            for (int t = 0; t < NC_CG; ++t)
+                if (!done[t] && acc >= vals[t]) { done[t] = true; atomicMin(&s.picks[t], i0 + e); }
+        }
+    }
+    __syncthreads();
+}
+
+// out[t][i] = squared distance of point i to candidate s.picks[t], t < nv
+__device__ void nc_dist_multi(const double* __restrict__ E, int N, int nv, NcSm& s, double* __restrict__ out) {
+    for (int idx = threadIdx.x; idx < nv * N; idx += NC_THREADS) {
+        const int t = idx / N, i = idx - t * N;
+        const double e = E[(size_t)s.picks[t] * N + i];
+        out[idx] = e * e;
+    }
+    __syncthreads();
+}
+
+// block sums of NC_CG values at once (all threads get all results)
+__device__ void nc_block_sum_multi(double (&v)[NC_CG], NcSm& s) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < NC_CG; ++t) v[t] = warp_sum(v[t]);
+    __syncthreads();
+    if (lane < NC_CG) {
+        double mine = v[0];
+#pragma unroll
+        for (int t = 1; t < NC_CG; ++t) mine = (lane == t) ? v[t] : mine;
+        s.red[wid * NC_CG + lane] = mine;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NC_CG; ++t) {
+        double a = 0.0;
+        for (int ww = 0; ww < NC_THREADS / 32; ++ww) a += s.red[ww * NC_CG + t];
+        v[t] = a;
+    }
 }
 
 // E-step: labels[i] = argmin_j (||c_j||^2 - 2 x_i.c_j), lowest j on ties.
@@ -131,8 +195,9 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
     s.cnew = s.centers + (size_t)max_k * N;
     s.xnorm = s.cnew + (size_t)max_k * N;
     s.closest = s.xnorm + N;
-    s.cand = s.closest + N;
-    s.colmean = s.cand + N;
+    s.cand = s.cnew;          // k-means++ candidate distances [ncg][N]: cnew is free until Lloyd starts
+    s.bestd = s.xnorm;
+    s.colmean = s.closest + N;
     s.cn2 = s.colmean + N;
     s.shift = s.cn2 + max_k;
     s.red = s.shift + max_k;
@@ -141,7 +206,17 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
     s.lbest = s.lold + N;
     s.counts = s.lbest + N;
     s.ired = s.counts + max_k;
-    __shared__ int s_flag, s_pick;
+    s.picks = s.ired + 32;
+    s.members = s.picks + NC_CG;
+    s.cstart = s.members + N;
+    __shared__ int s_flag;
+#ifdef NC_TIMING
+    long long nacc[6] = {0, 0, 0, 0, 0, 0}, nlast = clock64();
+    int niter = 0;
+#define NC_TICK(i) do { if (threadIdx.x == 0) { long long n__ = clock64(); nacc[i] += n__ - nlast; nlast = n__; } } while (0)
+#else
+#define NC_TICK(i) do { } while (0)
+#endif
     const int sim = blockIdx.x, tid = threadIdx.x;
     const double* X = Dall + (size_t)sim * N * N;   // symmetric: X[d][i] == X[i][d]; threads read "columns" coalesced
     const double* E = Eall + (size_t)sim * N * N;
@@ -159,82 +234,95 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
     }
     const double tol = 1e-4 * nc_block_sum(vsum, s) / N;
     __syncthreads();
-    for (int i = tid; i < N; i += NC_THREADS) {
-        double q = 0.0;
-        for (int d = 0; d < N; ++d) { double t = X[(size_t)d * N + i] - s.colmean[d]; q = fma(t, t, q); }
-        s.xnorm[i] = q;
-    }
-    __syncthreads();
 
     double best_q = NAN;
+    NC_TICK(0);
     for (int k = 2; k <= max_k; ++k) {
         const double* u = uni + (size_t)k * ustride;
         const int ntrials = 2 + (int)log((double)k);
         // ---- k-means++ ------------------------------------------------------------------------------------------------
-        if (tid == 0) {
-            // RandomState.choice(n, p=1/n): cdf = cumsum(p) / cdf[-1]; searchsorted(u, side='right')
-            double p = 1.0 / N, acc = 0.0, last = 0.0;
-            for (int i = 0; i < N; ++i) last += p;
-            int idx = N - 1;
-            for (int i = 0; i < N; ++i) { acc += p; if (!(acc / last <= u[0])) { idx = i; break; } }
-            s_pick = idx;
-        }
-        __syncthreads();
-        int first = s_pick;
+        // first centre: RandomState.choice(n, p=1/n) -- data independent, the index comes with the uniform table
+        const int first = (int)u[0];
         for (int d = tid; d < N; d += NC_THREADS) s.centers[d] = X[(size_t)d * N + first] - s.colmean[d];
-        nc_dist_to_point(X, s.colmean, N, first, s, s.closest);
+        nc_dist_to_point(E, N, first, s.closest);
         double pot = 0.0;
         for (int i = tid; i < N; i += NC_THREADS) pot += s.closest[i];
         pot = nc_block_sum(pot, s);
         for (int c = 1; c < k; ++c) {
             double best_pot = INFINITY;
             int best_id = -1;
-            for (int tr = 0; tr < ntrials; ++tr) {
-                if (tid == 0) {
-                    const double val = u[1 + (c - 1) * ntrials + tr] * pot;
-                    double acc = 0.0;
-                    int idx = N - 1;
-                    for (int i = 0; i < N; ++i) { acc += s.closest[i]; if (acc >= val) { idx = i; break; } }
-                    s_pick = idx;
+            const int ncg = min(NC_CG, max_k);
+            for (int t0 = 0; t0 < ntrials; t0 += ncg) {
+                const int nv = min(ncg, ntrials - t0);
+                double vals[NC_CG];
+#pragma unroll
+                for (int t = 0; t < NC_CG; ++t) vals[t] = (t < nv) ? u[1 + (c - 1) * ntrials + t0 + t] * pot : 0.0;
+                nc_pick_multi(s.closest, N, vals, nv, s);
+                nc_dist_multi(E, N, nv, s, s.cand);
+                double cp[NC_CG] = {0.0, 0.0, 0.0, 0.0};
+                for (int i = tid; i < N; i += NC_THREADS) {
+                    const double cl = s.closest[i];
+#pragma unroll
+                    for (int t = 0; t < NC_CG; ++t)
+                        if (t < nv) cp[t] += fmin(cl, s.cand[t * N + i]);
                 }
-                __syncthreads();
-                const int cid = s_pick;
-                nc_dist_to_point(X, s.colmean, N, cid, s, s.cand);
-                double cp = 0.0;
-                for (int i = tid; i < N; i += NC_THREADS) cp += fmin(s.closest[i], s.cand[i]);
-                cp = nc_block_sum(cp, s);
-                if (cp < best_pot) { best_pot = cp; best_id = cid; }  // np.argmin: first minimum
+                nc_block_sum_multi(cp, s);
+                int win = -1;
+#pragma unroll
+                for (int t = 0; t < NC_CG; ++t)
+                    if (t < nv && cp[t] < best_pot) { best_pot = cp[t]; best_id = s.picks[t]; win = t; }  // first minimum
+                if (win >= 0)
+                    for (int i = tid; i < N; i += NC_THREADS) s.bestd[i] = s.cand[win * N + i];
                 __syncthreads();
             }
-            nc_dist_to_point(X, s.colmean, N, best_id, s, s.cand);
-            for (int i = tid; i < N; i += NC_THREADS) s.closest[i] = fmin(s.closest[i], s.cand[i]);
+            for (int i = tid; i < N; i += NC_THREADS) s.closest[i] = fmin(s.closest[i], s.bestd[i]);
             for (int d = tid; d < N; d += NC_THREADS) s.centers[c * N + d] = X[(size_t)d * N + best_id] - s.colmean[d];
             pot = best_pot;
             __syncthreads();
         }
+        NC_TICK(1);
         // ---- Lloyd -----------------------------------------------------------------------------------------------------
         for (int i = tid; i < N; i += NC_THREADS) s.lold[i] = -1;
         __syncthreads();
         bool strict = false;
         for (int it = 0; it < NC_MAX_ITER; ++it) {
             nc_assign(X, N, k, s);
+            NC_TICK(2);
+#ifdef NC_TIMING
+            ++niter;
+#endif
             // M-step: new centres = mean of the members; empty clusters take the points farthest from their centres
             for (int j = tid; j < k; j += NC_THREADS) s.counts[j] = 0;
             __syncthreads();
             for (int i = tid; i < N; i += NC_THREADS) atomicAdd(&s.counts[s.labels[i]], 1);
             __syncthreads();
+            // points grouped by cluster (stable: thread j collects cluster j in ascending order), so a centre coordinate is a
+            // sum over its own members only instead of a predicated sum over all points
+            if (tid == 0) {
+                int acc = 0;
+                for (int j = 0; j < k; ++j) { s.cstart[j] = acc; acc += s.counts[j]; }
+                s.cstart[k] = acc;
+            }
+            __syncthreads();
+            for (int j = tid; j < k; j += NC_THREADS) {
+                int pos = s.cstart[j];
+                for (int i = 0; i < N; ++i)
+                    if (s.labels[i] == j) s.members[pos++] = i;
+            }
+            __syncthreads();
             for (int idx = tid; idx < k * N; idx += NC_THREADS) {
                 const int j = idx / N, d = idx % N;
-                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
                 const double cmd = s.colmean[d];
-                int i = 0;
-                for (; i + 3 < N; i += 4) {
-                    c0 += (s.labels[i] == j) ? X[(size_t)i * N + d] - cmd : 0.0;
-                    c1 += (s.labels[i + 1] == j) ? X[(size_t)(i + 1) * N + d] - cmd : 0.0;
-                    c2 += (s.labels[i + 2] == j) ? X[(size_t)(i + 2) * N + d] - cmd : 0.0;
-                    c3 += (s.labels[i + 3] == j) ? X[(size_t)(i + 3) * N + d] - cmd : 0.0;
+                const int e1 = s.cstart[j + 1];
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+                int e = s.cstart[j];
+                for (; e + 3 < e1; e += 4) {
+                    c0 += X[(size_t)s.members[e] * N + d] - cmd;
+                    c1 += X[(size_t)s.members[e + 1] * N + d] - cmd;
+                    c2 += X[(size_t)s.members[e + 2] * N + d] - cmd;
+                    c3 += X[(size_t)s.members[e + 3] * N + d] - cmd;
                 }
-                for (; i < N; ++i) c0 += (s.labels[i] == j) ? X[(size_t)i * N + d] - cmd : 0.0;
+                for (; e < e1; ++e) c0 += X[(size_t)s.members[e] * N + d] - cmd;
                 s.cnew[idx] = (c0 + c1) + (c2 + c3);
             }
             __syncthreads();
@@ -296,7 +384,9 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
             if (tot <= tol) break;
             for (int i = tid; i < N; i += NC_THREADS) s.lold[i] = s.labels[i];
             __syncthreads();
+            NC_TICK(3);
         }
+        NC_TICK(3);
         if (!strict) nc_assign(X, N, k, s);
         // ---- silhouette_samples (Euclidean between rows of D) and the quality mean/std --------------------------------
         double* dsum = s.cnew;  // [k][N] sum of distances from point i to the members of cluster j
@@ -338,9 +428,15 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
             for (int i = tid; i < N; i += NC_THREADS) s.lbest[i] = s.labels[i];
         }
         __syncthreads();
+        NC_TICK(4);
     }
+#ifdef NC_TIMING
+    if (tid == 0 && blockIdx.x == 0) printf("nco_cluster cycles: setup %lld kmeans++ %lld assign %lld mstep %lld silhouette %lld; lloyd iterations %d\n", nacc[0], nacc[1], nacc[2], nacc[3], nacc[4], niter);
+#endif
+    {
     for (int i = tid; i < N; i += NC_THREADS) labels_out[(size_t)sim * N + i] = s.lbest[i];
     if (tid == 0 && quality_out) quality_out[sim] = best_q;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -468,7 +564,7 @@ __global__ void __launch_bounds__(NC_THREADS) nco_alloc_kernel(const double* __r
 }
 
 // MT19937(42) uniform stream exactly as numpy.random.RandomState(42).random_sample() produces it
-static void nco_uniform_table(int max_k, int ustride, std::vector<double>& out) {
+static void nco_uniform_table(int max_k, int ustride, int n_points, std::vector<double>& out) {
     out.assign((size_t)(max_k + 1) * ustride, 0.0);
     for (int k = 2; k <= max_k; ++k) {
         std::mt19937 gen(42u);
@@ -478,6 +574,14 @@ static void nco_uniform_table(int max_k, int ustride, std::vector<double>& out) 
             uint32_t a = gen() >> 5, b = gen() >> 6;
             out[(size_t)k * ustride + i] = (a * 67108864.0 + b) / 9007199254740992.0;
         }
+        // slot 0 becomes the first centre itself: RandomState.choice(n, p=1/n) is cdf = cumsum(p) / cdf[-1];
+        // searchsorted(cdf, u, side='right') -- nothing in it depends on the data
+        const double u0 = out[(size_t)k * ustride], p = 1.0 / n_points;
+        double last = 0.0, acc = 0.0;
+        for (int i = 0; i < n_points; ++i) last += p;
+        int idx = n_points - 1;
+        for (int i = 0; i < n_points; ++i) { acc += p; if (!(acc / last <= u0)) { idx = i; break; } }
+        out[(size_t)k * ustride] = (double)idx;
     }
 }
 
@@ -507,13 +611,13 @@ int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, 
         const int ntr_max = 2 + (int)std::log((double)max_k);
         const int ustride = 1 + (max_k - 1) * ntr_max;
         std::vector<double> tab;
-        nco_uniform_table(max_k, ustride, tab);
+        nco_uniform_table(max_k, ustride, N, tab);
         double* duni;
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_NCO_E, tab.size(), &duni));
         MCOSB_CUDA(ctx, cudaMemcpyAsync(duni, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tab` is a pageable stack-owned buffer
-        size_t smem = (2 * (size_t)max_k * n + 4 * n + 2 * (size_t)max_k + 32) * sizeof(double) +
-                      (3 * n + (size_t)max_k + 32) * sizeof(int);
+        size_t smem = (2 * (size_t)max_k * n + 3 * n + 2 * (size_t)max_k + 32) * sizeof(double) +
+                      (4 * n + 2 * (size_t)max_k + 33 + NC_CG) * sizeof(int);
         if (smem > (size_t)ctx->smem_optin)
             return mcosb_fail(ctx, MCOSB_ERR_ARG, "max_num_clusters x n_assets too large for nco_cluster_kernel's shared memory");
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(nco_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
