@@ -41,6 +41,12 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, 
     const int sz = pred ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz));
 }
+// 16-byte variant (LDGSTS.128): both addresses must be 16-byte aligned
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, bool pred) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(sz));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
@@ -50,31 +56,51 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // CENTER: subtract per-column offsets (amean[mb], bmean[nb]) from the fragments as they are loaded -- the SYRK's
 // centring x - mean, done in registers so the tiles can be copied raw; only the first kvalid k-rows of the slab count
 // (rows beyond hold zero fill and must contribute nothing).
-template <bool A_KMAJOR, bool B_KMAJOR, bool CENTER>
+template <bool A_KMAJOR, bool B_KMAJOR, bool CENTER, bool RAGGED>
+__device__ __forceinline__ void dmma_kstep(const double* __restrict__ As, const double* __restrict__ Bs, int wm0,
+                                           int wn0, int lane, int k0, double (&acc)[DM_MB][DM_NB][2],
+                                           const double* amean, const double* bmean, int kvalid) {
+    const int g = lane >> 2, t = lane & 3;
+    double a[DM_MB], b[DM_NB];
+    const bool live = !RAGGED || (k0 + t < kvalid);
+#pragma unroll
+    for (int mb = 0; mb < DM_MB; ++mb) {
+        int m = wm0 + mb * 8 + g;
+        a[mb] = A_KMAJOR ? As[(k0 + t) * DM_LD_KMAJOR + m] : As[m * DM_LD_MMAJOR + k0 + t];
+        if (CENTER) a[mb] = a[mb] - amean[mb];
+        if (RAGGED) a[mb] = live ? a[mb] : 0.0;
+    }
+#pragma unroll
+    for (int nb = 0; nb < DM_NB; ++nb) {
+        int n = wn0 + nb * 8 + g;
+        b[nb] = B_KMAJOR ? Bs[(k0 + t) * DM_LD_KMAJOR + n] : Bs[n * DM_LD_MMAJOR + k0 + t];
+        if (CENTER) b[nb] = b[nb] - bmean[nb];
+        if (RAGGED) b[nb] = live ? b[nb] : 0.0;
+    }
+#pragma unroll
+    for (int mb = 0; mb < DM_MB; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < DM_NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+}
+
+// `mid()` runs after the first k-step: the cp.async issue of a later stage goes there, so that its address arithmetic
+// and LDGSTS instructions interleave with DMMAs already queued on the tensor pipe instead of idling it after the
+// barrier.  Slabs with kvalid >= DM_BK take the path without the per-fragment selects.
+template <bool A_KMAJOR, bool B_KMAJOR, bool CENTER, class Mid>
 __device__ __forceinline__ void dmma_slab(const double* __restrict__ As, const double* __restrict__ Bs, int wm0,
-                                          int wn0, int lane, double (&acc)[DM_MB][DM_NB][2],
+                                          int wn0, int lane, double (&acc)[DM_MB][DM_NB][2], Mid mid,
                                           const double* amean = nullptr, const double* bmean = nullptr,
                                           int kvalid = DM_BK) {
-    const int g = lane >> 2, t = lane & 3;
+    if (!CENTER || kvalid >= DM_BK) {
+        dmma_kstep<A_KMAJOR, B_KMAJOR, CENTER, false>(As, Bs, wm0, wn0, lane, 0, acc, amean, bmean, kvalid);
+        mid();
 #pragma unroll
-    for (int k0 = 0; k0 < DM_BK; k0 += 4) {
-        double a[DM_MB], b[DM_NB];
-        const bool live = !CENTER || (k0 + t < kvalid);
+        for (int k0 = 4; k0 < DM_BK; k0 += 4)
+            dmma_kstep<A_KMAJOR, B_KMAJOR, CENTER, false>(As, Bs, wm0, wn0, lane, k0, acc, amean, bmean, kvalid);
+    } else {
+        mid();
 #pragma unroll
-        for (int mb = 0; mb < DM_MB; ++mb) {
-            int m = wm0 + mb * 8 + g;
-            a[mb] = A_KMAJOR ? As[(k0 + t) * DM_LD_KMAJOR + m] : As[m * DM_LD_MMAJOR + k0 + t];
-            if (CENTER) a[mb] = live ? a[mb] - amean[mb] : 0.0;
-        }
-#pragma unroll
-        for (int nb = 0; nb < DM_NB; ++nb) {
-            int n = wn0 + nb * 8 + g;
-            b[nb] = B_KMAJOR ? Bs[(k0 + t) * DM_LD_KMAJOR + n] : Bs[n * DM_LD_MMAJOR + k0 + t];
-            if (CENTER) b[nb] = live ? b[nb] - bmean[nb] : 0.0;
-        }
-#pragma unroll
-        for (int mb = 0; mb < DM_MB; ++mb)
-#pragma unroll
-            for (int nb = 0; nb < DM_NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        for (int k0 = 0; k0 < DM_BK; k0 += 4)
+            dmma_kstep<A_KMAJOR, B_KMAJOR, CENTER, true>(As, Bs, wm0, wn0, lane, k0, acc, amean, bmean, kvalid);
     }
 }

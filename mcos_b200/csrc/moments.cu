@@ -44,6 +44,8 @@ __device__ __forceinline__ void tile_ij(int p, int& I, int& J) {
 
 // grid = (lower tiles, S).  lwpart[s][tile][2] receives (sum of squares of the scaled entries this tile stands for in
 // the full symmetric matrix, trace contribution).
+// VEC: 16-byte cp.async (N even and X 16-byte aligned), otherwise 8-byte copies.
+template <bool VEC>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T, int N, double scale,
             double* __restrict__ cov, double* __restrict__ lwpart) {
@@ -58,7 +60,9 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
-    const int lcol = tid % DM_BM, lk = tid / DM_BM;  // loader mapping: column fixed, k = lk + 2r
+    // loader mapping: VEC: column pair fixed, k = lk + 4r; otherwise column fixed, k = lk + 2r
+    constexpr int LW = VEC ? 2 : 1, LKS = DM_THREADS * LW / DM_BM;
+    const int lcol = (tid % (DM_BM / LW)) * LW, lk = tid / (DM_BM / LW);
     const int acol = I * DM_BM + lcol, bcol = J * DM_BN + lcol;
     const bool aok = acol < N, bok = bcol < N;
     const double* asrc = x + (aok ? acol : 0);
@@ -90,11 +94,17 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
         double* Bt = At + DM_TILE_KMAJOR;
         const int kbase = kt * DM_BK;
 #pragma unroll
-        for (int r = 0; r < DM_BK / 2; ++r) {
-            const int kk = lk + 2 * r, k = kbase + kk;
+        for (int r = 0; r < DM_BK / LKS; ++r) {
+            const int kk = lk + LKS * r, k = kbase + kk;
             const bool ok = k < T;
-            cp_async8(&At[kk * DM_LD_KMAJOR + lcol], asrc + (size_t)(ok ? k : 0) * N, ok && aok);
-            if (!diag) cp_async8(&Bt[kk * DM_LD_KMAJOR + lcol], bsrc + (size_t)(ok ? k : 0) * N, ok && bok);
+            const size_t goff = (size_t)(ok ? k : 0) * N;
+            if (VEC) {
+                cp_async16(&At[kk * DM_LD_KMAJOR + lcol], asrc + goff, ok && aok);
+                if (!diag) cp_async16(&Bt[kk * DM_LD_KMAJOR + lcol], bsrc + goff, ok && bok);
+            } else {
+                cp_async8(&At[kk * DM_LD_KMAJOR + lcol], asrc + goff, ok && aok);
+                if (!diag) cp_async8(&Bt[kk * DM_LD_KMAJOR + lcol], bsrc + goff, ok && bok);
+            }
         }
     };
     const int nkt = (T + DM_BK - 1) / DM_BK;
@@ -106,11 +116,13 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
-        if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
-        cp_async_commit();
         const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_KMAJOR;
         const double* Bt = diag ? At : At + DM_TILE_KMAJOR;
-        dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, amean, bmean, T - kt * DM_BK);
+        // the stage kt + 2 overwrites the buffer of slab kt - 1, which every warp has left (barrier above)
+        dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, [&] {
+            if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
+            cp_async_commit();
+        }, amean, bmean, T - kt * DM_BK);
     }
 
     // epilogue: scale, write the lower part and its mirror, accumulate Frobenius / trace partials
@@ -234,9 +246,14 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
     double* lwpart = nullptr;
     if (lw) MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWPART, (size_t)S * ntiles * 2, &lwpart));
     const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_KMAJOR * sizeof(double);
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double scale = lw ? 1.0 / T : 1.0 / (T - 1);
-    syrk_kernel<<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
+    if (N % 2 == 0 && (uintptr_t)dX % 16 == 0) {
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        syrk_kernel<true><<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
+    } else {
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        syrk_kernel<false><<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
+    }
     MCOSB_LAUNCHED(ctx, MK_SYRK);
 
     if (lw) {

@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(double* __restrict__
 }
 
 // X[m][j] = mu[j] + sum_{k <= j} Z[m][k] L[j][k];  M = S*T rows.  grid = (col tiles, row tiles)
+// VEC: 16-byte cp.async (N even, Z and L 16-byte aligned), otherwise 8-byte copies.
+template <bool VEC>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const double* __restrict__ mu, size_t M, int N,
             double* __restrict__ X) {
@@ -72,7 +74,9 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
     // quarters 0..3) take the same load off every scheduler
     const int cq = (wid >> 2) ? 3 - (wid & 3) : (wid & 3);
     const int wm0 = (wid >> 2) * DM_WM, wn0 = cq * DM_WN;
-    const int lk = tid % DM_BK, lr = tid / DM_BK;  // loader: k fixed, row = lr + 16 r
+    // loader: VEC: k pair fixed, row = lr + 32 r; otherwise k fixed, row = lr + 16 r
+    constexpr int LW = VEC ? 2 : 1, LRS = DM_THREADS * LW / DM_BK;
+    const int lk = (tid % (DM_BK / LW)) * LW, lr = tid / (DM_BK / LW);
 
     double acc[DM_MB][DM_NB][2];
 #pragma unroll
@@ -86,13 +90,18 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
         const int k = kt * DM_BK + lk;
         const bool kok = k < N;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int row = lr + 16 * r;
+        for (int r = 0; r < DM_BM / LRS; ++r) {
+            const int row = lr + LRS * r;
             const size_t m = m0 + row;
             const int j = J * DM_BN + row;
             const bool aok = kok && m < M, bok = kok && j < N;
-            cp_async8(&At[row * DM_LD_MMAJOR + lk], Z + (aok ? m * N + k : 0), aok);
-            cp_async8(&Bt[row * DM_LD_MMAJOR + lk], L + (bok ? (size_t)j * N + k : 0), bok);
+            if (VEC) {
+                cp_async16(&At[row * DM_LD_MMAJOR + lk], Z + (aok ? m * N + k : 0), aok);
+                cp_async16(&Bt[row * DM_LD_MMAJOR + lk], L + (bok ? (size_t)j * N + k : 0), bok);
+            } else {
+                cp_async8(&At[row * DM_LD_MMAJOR + lk], Z + (aok ? m * N + k : 0), aok);
+                cp_async8(&Bt[row * DM_LD_MMAJOR + lk], L + (bok ? (size_t)j * N + k : 0), bok);
+            }
         }
     };
     const int kend = min(N, (J + 1) * DM_BN);  // L[j][k] = 0 for k > j
@@ -105,11 +114,16 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
-        if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
-        cp_async_commit();
         const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_MMAJOR;
+        // the stage kt + 2 overwrites the buffer of slab kt - 1, which every warp has left (barrier above)
+        auto next = [&] {
+            if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
+            cp_async_commit();
+        };
         if (kt * DM_BK <= J * DM_BN + wn0 + DM_WN - 1)   // L[j][k] = 0 for k > j: nothing for this warp's columns
-            dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc);
+            dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc, next);
+        else
+            next();
     }
     const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
@@ -136,11 +150,17 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
     MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
     const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
     size_t row_tiles = (M + DM_BM - 1) / DM_BM;
     if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");
     dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
-    trmm_kernel<<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+    if (N % 2 == 0 && (uintptr_t)dZ % 16 == 0 && (uintptr_t)ctx->d_chol % 16 == 0) {
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        trmm_kernel<true><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+    } else {
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        trmm_kernel<false><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+    }
     MCOSB_LAUNCHED(ctx, MK_TRMM);
     return MCOSB_OK;
 }
