@@ -6,6 +6,7 @@
 // Operand tiles move global -> shared with cp.async (LDGSTS, 8-byte, zero-fill for the ragged edges) through a
 // DM_STAGES-deep ring, one __syncthreads per k-slab.
 #pragma once
+#include <type_traits>
 
 #define DM_BM 128
 #define DM_BN 128
@@ -102,5 +103,73 @@ __device__ __forceinline__ void dmma_slab(const double* __restrict__ As, const d
 #pragma unroll
         for (int k0 = 0; k0 < DM_BK; k0 += 4)
             dmma_kstep<A_KMAJOR, B_KMAJOR, CENTER, true>(As, Bs, wm0, wn0, lane, k0, acc, amean, bmean, kvalid);
+    }
+}
+
+// ---- diagonal tiles of a SYRK -------------------------------------------------------------------------------------------
+// Only the lower triangle of a diagonal 128 x 128 tile is needed: 10 of its 16 sub-blocks of 32 x 32, 4 of them (on the
+// diagonal) only as 10 of their 16 m8n8 blocks.  Warps 0..5 take one full sub-block each, warps 6 and 7 two diagonal
+// sub-blocks each: at most 20 DMMAs per warp and k-step instead of 32.  A and B fragments come from the same tile
+// (k-major).  Sub-tile U of the warp lives in acc[4 U .. 4 U + 3][*]; its means in amean / bmean[4 U .. 4 U + 3].
+template <bool TRI, bool RAGGED, int U>
+__device__ __forceinline__ void dmma_kstep_sub(const double* __restrict__ As, int r0, int c0, int lane, int k0,
+                                               double (&acc)[DM_MB][DM_NB][2], const double* amean,
+                                               const double* bmean, int kvalid) {
+    const int g = lane >> 2, t = lane & 3;
+    double a[4], b[4];
+    const bool live = !RAGGED || (k0 + t < kvalid);
+    const double* row = As + (k0 + t) * DM_LD_KMAJOR + g;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+        a[mb] = row[r0 + mb * 8] - amean[4 * U + mb];
+        if (RAGGED) a[mb] = live ? a[mb] : 0.0;
+    }
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        b[nb] = row[c0 + nb * 8] - bmean[4 * U + nb];
+        if (RAGGED) b[nb] = live ? b[nb] : 0.0;
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+            if (!TRI || nb <= mb) dmma_884(acc[4 * U + mb][nb][0], acc[4 * U + mb][nb][1], a[mb], b[nb]);
+}
+
+// sub-blocks (row, column in units of 32) of warp `wid` in a diagonal tile; two = warps 6, 7
+__device__ __forceinline__ void dmma_diag_subtiles(int wid, int& r0a, int& c0a, int& r0b, int& c0b) {
+    if (wid < 6) {
+        const int rb = wid < 3 ? wid + 1 : (wid < 5 ? wid - 1 : 3), cb = wid < 3 ? 0 : (wid < 5 ? 1 : 2);
+        r0a = 32 * rb; c0a = 32 * cb; r0b = r0a; c0b = c0a;
+    } else {
+        r0a = c0a = 64 * (wid - 6);
+        r0b = c0b = r0a + 32;
+    }
+}
+
+template <class Mid>
+__device__ __forceinline__ void dmma_slab_diag(const double* __restrict__ As, int wid, int lane,
+                                               double (&acc)[DM_MB][DM_NB][2], Mid mid, const double* amean,
+                                               const double* bmean, int kvalid) {
+    int r0a, c0a, r0b, c0b;
+    dmma_diag_subtiles(wid, r0a, c0a, r0b, c0b);
+    auto step = [&](int k0, auto ragged) {
+        constexpr bool R = decltype(ragged)::value;
+        if (wid < 6) {
+            dmma_kstep_sub<false, R, 0>(As, r0a, c0a, lane, k0, acc, amean, bmean, kvalid);
+        } else {
+            dmma_kstep_sub<true, R, 0>(As, r0a, c0a, lane, k0, acc, amean, bmean, kvalid);
+            dmma_kstep_sub<true, R, 1>(As, r0b, c0b, lane, k0, acc, amean, bmean, kvalid);
+        }
+    };
+    if (kvalid >= DM_BK) {
+        step(0, std::false_type{});
+        mid();
+#pragma unroll
+        for (int k0 = 4; k0 < DM_BK; k0 += 4) step(k0, std::false_type{});
+    } else {
+        mid();
+#pragma unroll
+        for (int k0 = 0; k0 < DM_BK; k0 += 4) step(k0, std::true_type{});
     }
 }

@@ -68,19 +68,22 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
     const double* asrc = x + (aok ? acol : 0);
     const double* bsrc = x + (bok ? bcol : 0);
 
-    // per-fragment column means (centring happens in registers, the tiles are copied raw)
-    double amean[DM_MB], bmean[DM_NB];
+    // per-fragment column means (centring happens in registers, the tiles are copied raw).  Diagonal tiles use the
+    // sub-tile decomposition of dmma_slab_diag: means of sub-tile U at [4 U .. 4 U + 3]
+    double amean[DM_MB], bmean[DM_MB];
+    int r0a = 0, c0a = 0, r0b = 0, c0b = 0;
+    if (diag) dmma_diag_subtiles(wid, r0a, c0a, r0b, c0b);
     {
         const int g = lane >> 2;
 #pragma unroll
         for (int mb = 0; mb < DM_MB; ++mb) {
-            int c = I * DM_BM + wm0 + mb * 8 + g;
+            int c = I * DM_BM + (diag ? (mb < 4 ? r0a : r0b - 32) : wm0) + mb * 8 + g;
             amean[mb] = (c < N) ? mu[c] : 0.0;
         }
 #pragma unroll
-        for (int nb = 0; nb < DM_NB; ++nb) {
-            int c = J * DM_BN + wn0 + nb * 8 + g;
-            bmean[nb] = (c < N) ? mu[c] : 0.0;
+        for (int nb = 0; nb < DM_MB; ++nb) {
+            int c = J * DM_BN + (diag ? (nb < 4 ? c0a : c0b - 32) : wn0) + nb * 8 + g;
+            bmean[nb] = (c < N && (diag || nb < DM_NB)) ? mu[c] : 0.0;
         }
     }
     double acc[DM_MB][DM_NB][2];
@@ -119,25 +122,29 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
         const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_KMAJOR;
         const double* Bt = diag ? At : At + DM_TILE_KMAJOR;
         // the stage kt + 2 overwrites the buffer of slab kt - 1, which every warp has left (barrier above)
-        dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, [&] {
+        auto next = [&] {
             if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
             cp_async_commit();
-        }, amean, bmean, T - kt * DM_BK);
+        };
+        if (diag) dmma_slab_diag(At, wid, lane, acc, next, amean, bmean, T - kt * DM_BK);
+        else dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, next, amean, bmean, T - kt * DM_BK);
     }
 
     // epilogue: scale, write the lower part and its mirror, accumulate Frobenius / trace partials
     const int g = lane >> 2, t4 = lane & 3;
     double* c = cov + (size_t)s * N * N;
     double frob = 0.0, tr = 0.0;
+    const bool two = diag && wid >= 6;
 #pragma unroll
     for (int mb = 0; mb < DM_MB; ++mb)
 #pragma unroll
         for (int nb = 0; nb < DM_NB; ++nb)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                int row = I * DM_BM + wm0 + mb * 8 + g;
-                int col = J * DM_BN + wn0 + nb * 8 + 2 * t4 + e;
-                if (row < N && col < N && col <= row) {
+                // diagonal tiles: accumulator rows 0..3 are sub-tile a, rows 4..7 sub-tile b (warps 6, 7 only)
+                int row = I * DM_BM + (diag ? (mb < 4 ? r0a + mb * 8 : r0b + (mb - 4) * 8) : wm0 + mb * 8) + g;
+                int col = J * DM_BN + (diag ? (mb < 4 ? c0a : c0b) : wn0) + nb * 8 + 2 * t4 + e;
+                if (row < N && col < N && col <= row && (!diag || mb < 4 || two)) {
                     double v = acc[mb][nb][e] * scale;
                     c[(size_t)row * N + col] = v;
                     if (col != row) {
