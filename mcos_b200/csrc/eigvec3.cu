@@ -197,16 +197,17 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
     }
 }
 
-// grid = (ceil(N / 32), S), 256 threads: the CTA stages the signal eigenvectors in shared memory once (they are re-read
+// grid = (ceil(N / 128), S), 256 threads: the CTA stages the signal eigenvectors in shared memory once (they are re-read
 // N / 32 times per simulation instead of N / 8 from L2), each warp owns 4 output rows and a lane walks the columns, so one
 // shared-memory load of v_sj feeds 4 FMAs.  r_i = lbar + sum_s c_s v_si^2 is the diagonal of the clipped matrix.
 #define RC_ROWS 4
+#define RC_CTA_ROWS 128   // rows per CTA: the staging of the eigenvectors is amortised over 128 x N outputs
 __global__ void __launch_bounds__(256) reconstruct_kernel(const double* __restrict__ V, const double* __restrict__ lamall,
                                                           const int* __restrict__ nfall,
                                                           const double* __restrict__ sigmaall, int N,
                                                           double* __restrict__ covall) {
     extern __shared__ double sm[];
-    double* rs = sm;             // [N] sqrt(r_j)
+    double* rs = sm;             // [N] 1 / sqrt(r_j)
     double* sg = sm + N;         // [N] sigma_j
     double* coef = sg + N;       // [EV3_VMAX]
     double* Vsm = coef + EV3_VMAX;   // [nf][N]
@@ -226,40 +227,42 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(const double* __restri
     for (int j = tid; j < N; j += 256) {
         double r = lbar;
         for (int s = 0; s < nf; ++s) { const double v = Vsm[s * N + j]; r = fma(coef[s] * v, v, r); }
-        rs[j] = sqrt(r);
+        rs[j] = 1.0 / sqrt(r);     // the division of the renormalisation becomes two multiplications per element
     }
     __syncthreads();
-    const int i0 = blockIdx.x * 32 + wid * RC_ROWS;
-    if (i0 >= N) return;
-    double a[RC_ROWS][EV3_VMAX], rsi[RC_ROWS], si[RC_ROWS];
-#pragma unroll
-    for (int r = 0; r < RC_ROWS; ++r) {
-        const int i = min(i0 + r, N - 1);
-        rsi[r] = rs[i];
-        si[r] = sg[i];
-#pragma unroll
-        for (int s = 0; s < EV3_VMAX; ++s) a[r][s] = (s < nf) ? coef[s] * Vsm[s * N + i] : 0.0;
-    }
     double* out = covall + (size_t)sim * N * N;
-    for (int j = lane; j < N; j += 32) {
-        double acc[RC_ROWS];
-#pragma unroll
-        for (int r = 0; r < RC_ROWS; ++r) acc[r] = (i0 + r == j) ? lbar : 0.0;
-#pragma unroll
-        for (int s = 0; s < EV3_VMAX; ++s) {
-            if (s < nf) {
-                const double v = Vsm[s * N + j];
-#pragma unroll
-                for (int r = 0; r < RC_ROWS; ++r) acc[r] = fma(a[r][s], v, acc[r]);
-            }
-        }
-        const double rsj = rs[j], sj = sg[j];
+    for (int rg = wid; rg < RC_CTA_ROWS / RC_ROWS; rg += 8) {
+        const int i0 = blockIdx.x * RC_CTA_ROWS + rg * RC_ROWS;
+        if (i0 >= N) break;
+        double a[RC_ROWS][EV3_VMAX], rsi[RC_ROWS], si[RC_ROWS];
 #pragma unroll
         for (int r = 0; r < RC_ROWS; ++r) {
-            if (i0 + r < N) {
-                double c = acc[r] / (rsi[r] * rsj);
-                c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
-                out[(size_t)(i0 + r) * N + j] = c * (si[r] * sj);
+            const int i = min(i0 + r, N - 1);
+            rsi[r] = rs[i];
+            si[r] = sg[i];
+#pragma unroll
+            for (int s = 0; s < EV3_VMAX; ++s) a[r][s] = (s < nf) ? coef[s] * Vsm[s * N + i] : 0.0;
+        }
+        for (int j = lane; j < N; j += 32) {
+            double acc[RC_ROWS];
+#pragma unroll
+            for (int r = 0; r < RC_ROWS; ++r) acc[r] = (i0 + r == j) ? lbar : 0.0;
+#pragma unroll
+            for (int s = 0; s < EV3_VMAX; ++s) {
+                if (s < nf) {
+                    const double v = Vsm[s * N + j];
+#pragma unroll
+                    for (int r = 0; r < RC_ROWS; ++r) acc[r] = fma(a[r][s], v, acc[r]);
+                }
+            }
+            const double rsj = rs[j], sj = sg[j];
+#pragma unroll
+            for (int r = 0; r < RC_ROWS; ++r) {
+                if (i0 + r < N) {
+                    double c = acc[r] * (rsi[r] * rsj);
+                    c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+                    out[(size_t)(i0 + r) * N + j] = c * (si[r] * sj);
+                }
             }
         }
     }
@@ -292,7 +295,7 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     const size_t smem = (2 * n + EV3_VMAX + EV3_VMAX * n) * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reconstruct_kernel<<<dim3((N + 31) / 32, S), 256, smem, ctx->stream>>>(V, lam, nf, sigma, N, cov);
+    reconstruct_kernel<<<dim3((N + RC_CTA_ROWS - 1) / RC_CTA_ROWS, S), 256, smem, ctx->stream>>>(V, lam, nf, sigma, N, cov);
     MCOSB_LAUNCHED(ctx, MK_RECONSTRUCT);
     return 1;
 }

@@ -65,17 +65,33 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
         }
         __syncthreads();
         const int kmax = min(EU_K, N - k0);
-        for (int kk = 0; kk < kmax; ++kk) {
-            double a[4], b[4];
+        if (I != J) {
+            for (int kk = 0; kk < kmax; ++kk) {
+                double a[4], b[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { a[q] = Si[kk][ty + 16 * q]; b[q] = Sj[kk][tx + 16 * q]; }  // lane-contiguous: no bank conflicts
+                for (int q = 0; q < 4; ++q) { a[q] = Si[kk][ty + 16 * q]; b[q] = Sj[kk][tx + 16 * q]; }  // lane-contiguous: no bank conflicts
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
+                for (int p = 0; p < 4; ++p)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    double df = __dsub_rn(a[p], b[q]);
-                    acc[p][q] = __dadd_rn(acc[p][q], __dmul_rn(df, df));
-                }
+                    for (int q = 0; q < 4; ++q) {
+                        double df = __dsub_rn(a[p], b[q]);
+                        acc[p][q] = __dadd_rn(acc[p][q], __dmul_rn(df, df));
+                    }
+            }
+        } else {
+            // diagonal tile: outputs (ty + 16 p, tx + 16 q) with q > p lie above the diagonal for every thread
+            for (int kk = 0; kk < kmax; ++kk) {
+                double a[4], b[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { a[q] = Si[kk][ty + 16 * q]; b[q] = Sj[kk][tx + 16 * q]; }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q <= p; ++q) {
+                        double df = __dsub_rn(a[p], b[q]);
+                        acc[p][q] = __dadd_rn(acc[p][q], __dmul_rn(df, df));
+                    }
+            }
         }
         __syncthreads();
     }
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             int i = I * EU_T + ty + 16 * p, j = J * EU_T + tx + 16 * q;
-            if (i < N && j < N) {
+            if (i < N && j < N && (I != J || j <= i)) {
                 double v = sqrt(acc[p][q]);
                 E[(size_t)i * N + j] = v;
                 E[(size_t)j * N + i] = v;
