@@ -19,23 +19,28 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
                          const double* Q2);
 
 // ---------------------------------------------------------------------------------------------------------------
-// D1: correlation matrix.  grid = (ceil(N/8), S), 256 threads, one warp per row.
+// D1: correlation matrix.  grid = (ceil(N/32), S), 256 threads, 4 rows per warp; the CTA takes the N square roots of
+// the diagonal once (strided reads) into shared memory instead of once per row.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) corr_kernel(const double* __restrict__ cov, int N, double* __restrict__ A,
                                                    double* __restrict__ sigma) {
+    extern __shared__ double sg[];   // [N]
     const int s = blockIdx.y;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= N) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double* c = cov + (size_t)s * N * N;
     double* a = A + (size_t)s * N * N;
-    const double si = sqrt(c[(size_t)row * N + row]);
-    if (lane == 0) sigma[(size_t)s * N + row] = si;
-    for (int j = lane; j < N; j += 32) {
-        double sj = sqrt(c[(size_t)j * N + j]);
-        double r = c[(size_t)row * N + j] / (si * sj);
-        r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);  // NaN passes through, as in numpy
-        a[(size_t)row * N + j] = r;
+    for (int j = threadIdx.x; j < N; j += 256) sg[j] = sqrt(c[(size_t)j * N + j]);
+    __syncthreads();
+    for (int r = 0; r < 4; ++r) {
+        const int row = blockIdx.x * 32 + wid * 4 + r;
+        if (row >= N) return;
+        const double si = sg[row];
+        if (lane == 0) sigma[(size_t)s * N + row] = si;
+        for (int j = lane; j < N; j += 32) {
+            double v = c[(size_t)row * N + j] / (si * sg[j]);
+            v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);  // NaN passes through, as in numpy
+            a[(size_t)row * N + j] = v;
+        }
     }
 }
 
@@ -869,7 +874,7 @@ int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, 
                           double* tau, double* lam, const double** q2) {
     const int N = ctx->N;
     const size_t n = (size_t)N;
-    corr_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, A, sigma);
+    corr_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, A, sigma);
     MCOSB_LAUNCHED(ctx, MK_CORR);
     MCOSB_TRY(mcosb_dev_tridiagonalize(ctx, S, A, d, e, tau, q2));
     size_t smem_ev = 2 * n * sizeof(double) + n * sizeof(int);

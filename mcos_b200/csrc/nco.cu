@@ -22,19 +22,23 @@
 #define NC_MAX_ITER 300
 
 __global__ void __launch_bounds__(256) nco_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D) {
+    extern __shared__ double sg[];   // [N] square roots of the diagonal, once per CTA (32 rows)
     const int s = blockIdx.y;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= N) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double* c = cov + (size_t)s * N * N;
     double* d = D + (size_t)s * N * N;
-    const double si = sqrt(c[(size_t)row * N + row]);
-    for (int j = lane; j < N; j += 32) {
-        double sj = sqrt(c[(size_t)j * N + j]);
-        double r = __ddiv_rn(c[(size_t)row * N + j], __dmul_rn(si, sj));
-        r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-        if (r != r) r = 0.0;  // corr.fillna(0)
-        d[(size_t)row * N + j] = sqrt(__ddiv_rn(__dsub_rn(1.0, r), 2.0));
+    for (int j = threadIdx.x; j < N; j += 256) sg[j] = sqrt(c[(size_t)j * N + j]);
+    __syncthreads();
+    for (int q = 0; q < 4; ++q) {
+        const int row = blockIdx.x * 32 + wid * 4 + q;
+        if (row >= N) return;
+        const double si = sg[row];
+        for (int j = lane; j < N; j += 32) {
+            double r = __ddiv_rn(c[(size_t)row * N + j], __dmul_rn(si, sg[j]));
+            r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+            if (r != r) r = 0.0;  // corr.fillna(0)
+            d[(size_t)row * N + j] = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
+        }
     }
 }
 
@@ -604,7 +608,7 @@ int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, 
         double *D, *E;
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_WORK, (size_t)S * n * n, &D));
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_E, (size_t)S * n * n, &E));
-        nco_dist_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, N, D);
+        nco_dist_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, D);
         MCOSB_LAUNCHED(ctx, MK_NCO_DIST);
         mcosb_launch_euclid(ctx, S, D, E);
         MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
