@@ -67,15 +67,27 @@ __device__ __forceinline__ void dmma_kstep(const double* __restrict__ As, const 
 #pragma unroll
     for (int mb = 0; mb < DM_MB; ++mb) {
         int m = wm0 + mb * 8 + g;
+#if defined(DM_ABLATE) && (DM_ABLATE & 1)   // timing experiment only: no shared-memory operand loads
+        a[mb] = __hiloint2double(0x3ff00000 + m, k0);
+#else
         a[mb] = A_KMAJOR ? As[(k0 + t) * DM_LD_KMAJOR + m] : As[m * DM_LD_MMAJOR + k0 + t];
+#endif
+#if !(defined(DM_ABLATE) && (DM_ABLATE & 2))   // timing experiment only: no centring
         if (CENTER) a[mb] = a[mb] - amean[mb];
+#endif
         if (RAGGED) a[mb] = live ? a[mb] : 0.0;
     }
 #pragma unroll
     for (int nb = 0; nb < DM_NB; ++nb) {
         int n = wn0 + nb * 8 + g;
+#if defined(DM_ABLATE) && (DM_ABLATE & 1)
+        b[nb] = __hiloint2double(0x3ff00000 + n, k0);
+#else
         b[nb] = B_KMAJOR ? Bs[(k0 + t) * DM_LD_KMAJOR + n] : Bs[n * DM_LD_MMAJOR + k0 + t];
+#endif
+#if !(defined(DM_ABLATE) && (DM_ABLATE & 2))
         if (CENTER) b[nb] = b[nb] - bmean[nb];
+#endif
         if (RAGGED) b[nb] = live ? b[nb] : 0.0;
     }
 #pragma unroll

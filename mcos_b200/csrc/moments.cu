@@ -51,6 +51,9 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
             double* __restrict__ cov, double* __restrict__ lwpart) {
     extern __shared__ double sm[];
     __shared__ double red[32];
+#ifdef SYRK_TIMING
+    const long long tk0 = clock64();
+#endif
     const int s = blockIdx.y;
     int I, J;
     tile_ij(blockIdx.x, I, J);
@@ -93,6 +96,9 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
         for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     auto issue = [&](int kt, int buf) {
+#if defined(DM_ABLATE) && (DM_ABLATE & 4)   // timing experiment only: no global -> shared copies
+        return;
+#endif
         double* At = sm + (size_t)buf * 2 * DM_TILE_KMAJOR;
         double* Bt = At + DM_TILE_KMAJOR;
         const int kbase = kt * DM_BK;
@@ -111,6 +117,10 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
         }
     };
     const int nkt = (T + DM_BK - 1) / DM_BK;
+#ifdef SYRK_TIMING
+    const long long tk1 = clock64();
+    long long tk2 = 0;
+#endif
 #pragma unroll
     for (int st = 0; st < DM_STAGES - 1; ++st) {
         if (st < nkt) issue(st, st);
@@ -119,6 +129,9 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
+#ifdef SYRK_TIMING
+        if (kt == 0) tk2 = clock64();
+#endif
         const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_KMAJOR;
         const double* Bt = diag ? At : At + DM_TILE_KMAJOR;
         // the stage kt + 2 overwrites the buffer of slab kt - 1, which every warp has left (barrier above)
@@ -130,6 +143,9 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
         else dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, next, amean, bmean, T - kt * DM_BK);
     }
 
+#ifdef SYRK_TIMING
+    const long long tk3 = clock64();
+#endif
     // epilogue: scale, write the lower part and its mirror, accumulate Frobenius / trace partials
     const int g = lane >> 2, t4 = lane & 3;
     double* c = cov + (size_t)s * N * N;
@@ -165,6 +181,11 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
             lwpart[o + 1] = tr;
         }
     }
+#ifdef SYRK_TIMING
+    if (tid == 0 && s == 1 && blockIdx.x < 10)
+        printf("syrk tile %d (I %d J %d): setup %lld fill %lld mainloop %lld epilogue %lld cycles\n", blockIdx.x, I, J,
+               tk1 - tk0, tk2 - tk1, tk3 - tk2, clock64() - tk3);
+#endif
 }
 
 // Ledoit-Wolf beta_raw = sum_t (sum_i xc_ti^2)^2, partial per chunk of rows.  grid = (row chunks, S)

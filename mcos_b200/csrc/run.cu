@@ -7,6 +7,12 @@
 
 #include "common.cuh"
 
+// X and Z of the sampling + moments stage are materialised per sub-chunk of this many bytes (each); larger chunks mean
+// fewer, longer SYRK / TRMM launches (less tail), at 2 x this much HBM
+#ifndef RUN_CHUNK_BYTES
+#define RUN_CHUNK_BYTES ((size_t)4 << 30)
+#endif
+
 int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W, const double* d_ideal, double* derr,
                    int* dstatus, std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>& marks) {
     const size_t N = ctx->N, T = ctx->T;
@@ -23,7 +29,7 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
     };
     MCOSB_PROFILE_MARK(ctx);
     // ---- sampling + moments in sub-chunks so X (8TN bytes per simulation) stays small ---------------------------------
-    const size_t chunk_bytes = (size_t)1 << 30;
+    const size_t chunk_bytes = RUN_CHUNK_BYTES;
     int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)W, chunk_bytes / (T * N * sizeof(double))));
     double* dX;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * T * N, &dX));
@@ -147,7 +153,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
         // per simulation: cov + denoise work matrix + HRP D and E (4 N^2), inverse-iteration scratch, small vectors
         size_t per_sim = (5 * N * N + 6 * N * 16 + 16 * N) * sizeof(double);
         size_t budget = (free_b + held) / 2;
-        size_t fixed = 2 * ((size_t)1 << 30) + ((size_t)1 << 28);  // X + Z chunk buffers
+        size_t fixed = 2 * RUN_CHUNK_BYTES + ((size_t)1 << 28);  // X + Z chunk buffers
         size_t w = budget > fixed ? (budget - fixed) / per_sim : 1;
         wave = (int)std::max<size_t>(1, std::min<size_t>(w, 8192));
     }

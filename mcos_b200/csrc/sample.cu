@@ -85,6 +85,9 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
         for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     auto issue = [&](int kt, int buf) {
+#if defined(DM_ABLATE) && (DM_ABLATE & 4)   // timing experiment only: no global -> shared copies
+        return;
+#endif
         double* At = sm + (size_t)buf * 2 * DM_TILE_MMAJOR;
         double* Bt = At + DM_TILE_MMAJOR;
         const int k = kt * DM_BK + lk;

@@ -110,9 +110,26 @@ def gather_errors(local: np.ndarray, n_sims: int, device=None) -> np.ndarray:
     return np.concatenate(parts, axis=0)
 
 
+def _plan_signature(plan, obs_simulator, n_sims, lo, hi, sim_id0) -> str:
+    """What a checkpoint must agree on to be resumed: the stage plan, the truth, the seed and the id range."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(bytes(plan))
+    h.update(np.ascontiguousarray(np.asarray(obs_simulator.mu, dtype=np.float64)).tobytes())
+    h.update(np.ascontiguousarray(np.asarray(obs_simulator.cov, dtype=np.float64)).tobytes())
+    h.update(repr((int(obs_simulator.n_observations), int(getattr(obs_simulator, "seed", 0)), int(n_sims), int(lo),
+                   int(hi), int(sim_id0))).encode())
+    return h.hexdigest()
+
+
 def simulate_errors(obs_simulator, n_sims, optimizers, error_estimator, covariance_transformers, *, device: int = None,
-                    wave: int = 0, sim_id0: int = 0):
-    """Per-simulation errors [n_sims, n_optimizers] (all ranks' shards gathered) and status words of the local shard."""
+                    wave: int = 0, sim_id0: int = 0, checkpoint: str = None, checkpoint_every: int = 8192):
+    """Per-simulation errors [n_sims, n_optimizers] (all ranks' shards gathered) and status words of the local shard.
+
+    `checkpoint` (for the million-simulation configurations): path prefix of a per-rank file
+    `<checkpoint>.rank<r>.npz` rewritten after every `checkpoint_every` simulations of the local shard.  A run started
+    with the same plan, truth, seed and id range picks up after the last completed chunk; the simulations are keyed by
+    id (Philox counter), so a resumed run returns exactly what an uninterrupted one would."""
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
     if device is None:
@@ -122,13 +139,55 @@ def simulate_errors(obs_simulator, n_sims, optimizers, error_estimator, covarian
     eng = get_engine(n, obs_simulator.n_observations, device, getattr(obs_simulator, "seed", 0))
     eng.ensure_truth(obs_simulator.mu, obs_simulator.cov)
     lo, hi = shard_range(n_sims, rank, world)
-    err, status = eng.run(plan, hi - lo, sim_id0 + lo)
+    if checkpoint is None:
+        err, status = eng.run(plan, hi - lo, sim_id0 + lo)
+    else:
+        import os
+        path = f"{checkpoint}.rank{rank}.npz"
+        sig = _plan_signature(plan, obs_simulator, n_sims, lo, hi, sim_id0)
+        err = np.full((hi - lo, len(optimizers)), np.nan)
+        status = np.zeros(hi - lo, dtype=np.int32)
+        done = 0
+        if os.path.exists(path):
+            with np.load(path, allow_pickle=False) as z:
+                if str(z["signature"]) == sig:
+                    done = int(z["done"])
+                    err[:done], status[:done] = z["errors"][:done], z["status"][:done]
+        step = max(1, int(checkpoint_every))
+        while done < hi - lo:
+            m = min(step, hi - lo - done)
+            err[done:done + m], status[done:done + m] = eng.run(plan, m, sim_id0 + lo + done)
+            done += m
+            tmp = path + ".tmp.npz"
+            np.savez(tmp, signature=np.array(sig), done=np.array(done), errors=err[:done], status=status[:done])
+            os.replace(tmp, path)
     bad = status & (_lib.ST_HRP_SUM | _lib.ST_NO_EXCESS)
     if bad.any():  # the reference aborts the whole run on these (optimizer.py:220-221)
         if (bad & _lib.ST_HRP_SUM).any():
             raise ValueError("Portfolio allocations don't sum to 1.")
         raise ValueError("no asset has an expected return above the risk-free rate")
     return gather_errors(err, n_sims, device), status
+
+
+def summarize_errors(errors: np.ndarray, optimizers: List[AbstractOptimizer], confidence: float = 0.95) -> pd.DataFrame:
+    """Per-optimizer summary of a per-simulation error dump: `mean` and `stdev` are the reference's
+    columns (np.mean / np.std with ddof = 0 over ALL simulations, so a NaN propagates exactly as it does in
+    mcos/mcos.py:36-40); next to them the NaN accounting (the Sharpe estimator yields NaN when the allocation equals the
+    ideal one, error_estimator.py:41) and NaN-excluded statistics with a normal-approximation confidence interval of
+    the mean."""
+    from statistics import NormalDist
+    z = NormalDist().inv_cdf(0.5 + confidence / 2.0)
+    rows = []
+    for i, opt in enumerate(optimizers):
+        e = np.asarray(errors[:, i], dtype=np.float64)
+        ok = e[~np.isnan(e)]
+        m = float(ok.mean()) if ok.size else np.nan
+        sd = float(ok.std(ddof=1)) if ok.size > 1 else np.nan
+        se = sd / np.sqrt(ok.size) if ok.size > 1 else np.nan
+        rows.append({'optimizer': opt.name, 'mean': np.mean(e), 'stdev': np.std(e), 'n_sims': int(e.size),
+                     'n_nan': int(e.size - ok.size), 'mean_valid': m, 'stderr': se, 'ci_low': m - z * se,
+                     'ci_high': m + z * se})
+    return pd.DataFrame(rows).set_index('optimizer')
 
 
 def simulate_optimizations(

@@ -138,3 +138,30 @@ def test_unknown_plugin_types_raise():
 
     with pytest.raises(TypeError):
         mb.simulate_optimizations(sim, 4, [MyOpt()], mb.VarianceErrorEstimator(), [])
+
+
+@pytest.mark.gpu
+def test_checkpointed_run_resumes_exactly(tmp_path):
+    """a run cut off after a chunk and restarted returns what the uninterrupted run returns (simulations
+    are keyed by id); a checkpoint of a different run is ignored."""
+    mu, cov = block_diagonal_truth(40)
+    sim = mb.MuCovLedoitWolfObservationSimulator(mu, cov, 80)
+    args = (sim, 300, [mb.MarkowitzOptimizer(), mb.HRPOptimizer()], mb.SharpeRatioErrorEstimator(),
+            [mb.DeNoiserCovarianceTransformer()])
+    ref, st_ref = mb.simulate_errors(*args)
+    ck = str(tmp_path / "run")
+    full, st = mb.simulate_errors(*args, checkpoint=ck, checkpoint_every=128)
+    np.testing.assert_array_equal(full, ref)
+    np.testing.assert_array_equal(st, st_ref)
+    path = ck + ".rank0.npz"
+    z = dict(np.load(path))
+    assert int(z["done"]) == 300
+    # pretend the run died after the first chunk, with rubbish where the later chunks would go
+    np.savez(path, signature=z["signature"], done=np.array(128), errors=z["errors"][:128], status=z["status"][:128])
+    resumed, st2 = mb.simulate_errors(*args, checkpoint=ck, checkpoint_every=128)
+    np.testing.assert_array_equal(resumed, ref)
+    np.testing.assert_array_equal(st2, st_ref)
+    # a checkpoint of another run (different truth) must not be picked up
+    np.savez(path, signature=np.array("something else"), done=np.array(300), errors=np.zeros_like(ref), status=st_ref)
+    again, _ = mb.simulate_errors(*args, checkpoint=ck, checkpoint_every=128)
+    np.testing.assert_array_equal(again, ref)

@@ -165,3 +165,24 @@ def test_lbfgsb_1d_restatement_matches_scipy():
         out = minimize(lambda v: oracle.mp_fit_objective(v, lam, 2.0), .5, bounds=((1e-5, 1 - 1e-5),))
         xm, ok, it, nfev = lbfgsb_1d(make_obj(lam, 2.0))
         assert ok and out.success and it == out.nit and abs(xm - out.x[0]) < 1e-6
+
+
+def test_summarize_errors_nan_accounting_and_interval():
+    """`mean` / `stdev` stay the reference's (a NaN propagates as in mcos/mcos.py:36-40); the NaN count and
+    NaN-excluded statistics sit next to them."""
+    import mcos_b200 as mb
+    rng = np.random.RandomState(3)
+    e = rng.normal(1.0, 2.0, size=(4000, 2))
+    e[5, 1] = np.nan
+    e[77, 1] = np.nan
+    df = mb.summarize_errors(e, [mb.MarkowitzOptimizer(), mb.HRPOptimizer()])
+    assert list(df.index) == ["markowitz", "HRP"]
+    assert df.loc["markowitz", "mean"] == np.mean(e[:, 0]) and df.loc["markowitz", "stdev"] == np.std(e[:, 0])
+    assert df.loc["markowitz", "n_nan"] == 0 and df.loc["HRP", "n_nan"] == 2 and df.loc["HRP", "n_sims"] == 4000
+    assert np.isnan(df.loc["HRP", "mean"]) and np.isnan(df.loc["HRP", "stdev"])
+    ok = e[~np.isnan(e[:, 1]), 1]
+    assert df.loc["HRP", "mean_valid"] == pytest.approx(ok.mean(), rel=1e-15)
+    se = ok.std(ddof=1) / np.sqrt(ok.size)
+    assert df.loc["HRP", "stderr"] == pytest.approx(se, rel=1e-14)
+    assert df.loc["HRP", "ci_high"] - df.loc["HRP", "ci_low"] == pytest.approx(2 * 1.959963984540054 * se, rel=1e-12)
+    assert df.loc["markowitz", "ci_low"] < 1.0 < df.loc["markowitz", "ci_high"]
