@@ -14,7 +14,7 @@
 enum ScratchSlot {
     SL_STAGE_IN0 = 0, SL_STAGE_IN1, SL_STAGE_IN2, SL_STAGE_IN3,
     SL_STAGE_OUT0, SL_STAGE_OUT1, SL_STAGE_OUT2, SL_STAGE_OUT3, SL_STAGE_OUT4,
-    SL_Z, SL_X, SL_MUHAT, SL_COV, SL_COLMEAN, SL_LWPART, SL_LWSTAT,
+    SL_Z, SL_X, SL_MUHAT, SL_COV, SL_COLMEAN, SL_LWPART, SL_LWSTAT, SL_LWCOEF,
     SL_DN_A, SL_DN_SIGMA, SL_DN_D, SL_DN_E, SL_DN_TAU, SL_DN_LAM, SL_DN_VAR, SL_DN_NF, SL_DN_VEC, SL_DN_WORK,
     SL_MK_L, SL_MK_W, SL_MK_ITERS,
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
@@ -286,17 +286,27 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+// Ledoit-Wolf shrink of one covariance entry, (1 - sh) c (+ sh m on the diagonal).  Spelled with explicit roundings so
+// that lw_finish_kernel (in place) and corr_kernel (on the fly, fused loop) produce the same bits.
+__device__ __forceinline__ double lw_shrink(double c, double sh, double m, bool diag) {
+    const double v = __dmul_rn(__dsub_rn(1.0, sh), c);
+    return diag ? __fma_rn(sh, m, v) : v;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // internal (device-pointer) stage entry points used by the public wrappers and by mcosb_run
 // ---------------------------------------------------------------------------------------------------------------
 int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX);
-int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink);
+// lwcoef_defer (Ledoit-Wolf only): instead of shrinking dcov in place, leave S_b there and write (shrinkage, mean
+// variance) per simulation to lwcoef_defer[2 s .. 2 s + 1]; mcosb_dev_denoise applies them while it forms the correlation
+int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink,
+                      double* lwcoef_defer = nullptr);
 int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
-                      int* dnf, int* dstatus);
+                      int* dnf, int* dstatus, const double* lwcoef = nullptr);
 // *q2 receives the stage-2 reflectors when the two-stage tridiagonalisation was used (then A holds the panel reflectors
 // of sy2sb_kernel, offset 8), nullptr for the one-stage kernels (offset 1)
 int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, double* sigma, double* d, double* e,
-                          double* tau, double* lam, const double** q2);
+                          double* tau, double* lam, const double** q2, const double* lwcoef = nullptr);
 int mcosb_dev_detone(mcosb_ctx* ctx, int S, double* dcov, int n_remove, int* dstatus);
 int mcosb_dev_risk_parity(mcosb_ctx* ctx, int S, const double* dcov, const double* dbudget, double* dw, int* diters,
                           int* dstatus);

@@ -245,11 +245,29 @@ __global__ void __launch_bounds__(256) lw_finish_kernel(double* __restrict__ cov
     for (int i = blockIdx.y * nw + wid; i < N; i += gridDim.y * nw) {
         double* row = c + (size_t)i * N;
         for (int j = lane; j < N; j += 32) {
-            double v = (1.0 - sh) * row[j];
-            if (j == i) v += sh * m;
-            row[j] = v;
+            row[j] = lw_shrink(row[j], sh, m, j == i);
         }
     }
+}
+
+// The Ledoit-Wolf coefficients alone (same sums, same order as lw_finish_kernel): (shrinkage, mean variance) per
+// simulation, for consumers that apply the shrink themselves (corr_kernel of the de-noiser).  One thread per simulation.
+__global__ void lw_coef_kernel(const double* __restrict__ lwpart, int ntiles, const double* __restrict__ rnpart,
+                               int nchunks, int T, int N, int S, double* __restrict__ coef) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double delta_raw = 0.0, tr = 0.0, beta_raw = 0.0;
+    for (int i = 0; i < ntiles; ++i) {
+        delta_raw += lwpart[((size_t)s * ntiles + i) * 2];
+        tr += lwpart[((size_t)s * ntiles + i) * 2 + 1];
+    }
+    for (int i = 0; i < nchunks; ++i) beta_raw += rnpart[(size_t)s * nchunks + i];
+    double m = tr / N;
+    double beta = (beta_raw / T - delta_raw) / ((double)N * T);
+    double delta = (delta_raw - N * m * m) / N;
+    beta = fmin(beta, delta);
+    coef[2 * (size_t)s] = (beta == 0.0) ? 0.0 : beta / delta;
+    coef[2 * (size_t)s + 1] = m;
 }
 
 __global__ void fill_kernel(double* p, size_t n, double v) {
@@ -257,7 +275,8 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
     if (i < n) p[i] = v;
 }
 
-int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink) {
+int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink,
+                      double* lwcoef_defer) {
     if (kind < 0 || kind > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown moments kind");
     if (S == 0) return MCOSB_OK;
     const int N = ctx->N, T = ctx->T;
@@ -290,7 +309,11 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWSTAT, (size_t)S * nchunks, &rnpart));
         lw_rownorm_kernel<<<dim3(nchunks, S), 256, 0, ctx->stream>>>(dX, dmu, T, N, rnpart);
         MCOSB_LAUNCHED(ctx, MK_LW_ROWNORM);
-        lw_finish_kernel<<<dim3(S, 8), 256, 0, ctx->stream>>>(dcov, lwpart, ntiles, rnpart, nchunks, T, N, dshrink);
+        if (lwcoef_defer) {
+            lw_coef_kernel<<<(S + 127) / 128, 128, 0, ctx->stream>>>(lwpart, ntiles, rnpart, nchunks, T, N, S, lwcoef_defer);
+        } else {
+            lw_finish_kernel<<<dim3(S, 8), 256, 0, ctx->stream>>>(dcov, lwpart, ntiles, rnpart, nchunks, T, N, dshrink);
+        }
         MCOSB_LAUNCHED(ctx, MK_LW_FINISH);
     } else if (dshrink) {
         fill_kernel<<<(S + 255) / 256, 256, 0, ctx->stream>>>(dshrink, (size_t)S, 0.0);

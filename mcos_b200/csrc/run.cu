@@ -33,6 +33,11 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
     int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)W, chunk_bytes / (T * N * sizeof(double))));
     double* dX;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * T * N, &dX));
+    // Ledoit-Wolf followed by the de-noiser: the shrink (one read-modify-write of every covariance matrix) is folded
+    // into the de-noiser's covariance -> correlation pass, which is the only consumer of the shrunk matrix
+    double* lwcoef = nullptr;
+    if (plan->moments_kind == MCOSB_MOMENTS_LEDOIT_WOLF && plan->denoise)
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWCOEF, 2 * (size_t)W, &lwcoef));
     for (int c0 = 0; c0 < W; c0 += CH) {
         const int nc = std::min(CH, W - c0);
         MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, true));
@@ -40,12 +45,12 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
         MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, false));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, true));
         MCOSB_TRY(mcosb_dev_moments(ctx, nc, dX, plan->moments_kind, dmu + (size_t)c0 * N, dcov + (size_t)c0 * N * N,
-                                    nullptr));
+                                    nullptr, lwcoef ? lwcoef + 2 * (size_t)c0 : nullptr));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, false));
     }
     if (plan->denoise) {
         MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, true));
-        MCOSB_TRY(mcosb_dev_denoise(ctx, W, dcov, ctx->T, plan->bandwidth, nullptr, nullptr, nullptr, dstatus));
+        MCOSB_TRY(mcosb_dev_denoise(ctx, W, dcov, ctx->T, plan->bandwidth, nullptr, nullptr, nullptr, dstatus, lwcoef));
         MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, false));
     }
     if (plan->detone_n_remove > 0) {
