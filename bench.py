@@ -71,7 +71,8 @@ def kernel_models(n, t):
         "reconstruct": ("hbm", 8.0 * n * n, "B"),                         # de-noised covariance written once
         "markowitz": ("hbm", 8.0 * n * 50 * 60, "B"),                     # ~60 iterations x |F|~50 rows of C from L2
         "hrp_dist": ("hbm", 16.0 * n * n, "B"),
-        "hrp_euclid": ("fp64_nofma", 3.0 * n3 / 2, "instr"),              # sub, mul, add per (i<j, k): bit-exact, no FMA
+        "hrp_gram": ("tensor", n3, "flop"),                               # lower triangle of D D' on DMMA (fast path)
+        "hrp_euclid": ("fp64_nofma", 3.0 * n3 / 2, "instr"),              # sub, mul, add per (i<j, k): exact fallback only
         "hrp_tree": ("hbm", 8.0 * n * n, "B"),                            # Prim reads every row of E once
         "hrp_permute": ("hbm", 16.0 * n * n, "B"),                        # covariance gathered into quasi-diagonal order
         "hrp_bisect": ("hbm", 16.0 * n * n, "B"),                         # every level reads its diagonal blocks: 2 N^2 total

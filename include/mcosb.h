@@ -113,6 +113,17 @@ int mcosb_markowitz(mcosb_ctx* ctx, int S, const double* mu, const double* cov, 
  * it.  Nullable: order[S][N] (asset index at each position), linkage[S][N-1][4] (scipy layout), status[S]. */
 int mcosb_hrp(mcosb_ctx* ctx, int S, const double* cov, double* w, int* order, double* linkage, int* status);
 
+/* How mcosb_hrp / mcosb_run obtain scipy's single-linkage tree (sch.linkage on the square distance matrix,
+ * optimizer.py:216).  0 (default): approximate squared row distances on the FP64 tensor cores, Prim's algorithm with
+ * every comparison guarded by a rigorous error bound, merge heights recomputed with scipy's arithmetic; a simulation
+ * with any comparison inside the bound is redone with exact distances, so the linkage is scipy's bit for bit either
+ * way.  1: exact distances (scipy's pdist arithmetic) for every simulation.  2: as 0 with every simulation sent to the
+ * exact fallback (test aid). */
+int mcosb_set_hrp_mode(mcosb_ctx* ctx, int mode);
+
+/* Number of simulations that took the exact fallback since the last call (host int; synchronises the stream). */
+int mcosb_hrp_fallback_count(mcosb_ctx* ctx, int* count);
+
 /* NCOOptimizer.allocate (optimizer.py:74-138).  mu nullable (minimum-variance variant).  labels_in[S][N] nullable:
  * when given, the KMeans/silhouette search (optimizer.py:140-174) is skipped and this partition is used.
  * Nullable: labels_out[S][N], status[S]. */

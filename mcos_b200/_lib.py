@@ -47,6 +47,8 @@ SIGNATURES = {
     "mcosb_detone": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "mcosb_markowitz": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "mcosb_hrp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcosb_set_hrp_mode": (c_int, [c_void_p, c_int]),
+    "mcosb_hrp_fallback_count": (c_int, [c_void_p, POINTER(c_int)]),
     "mcosb_nco": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_risk_parity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_errors": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -25,7 +25,8 @@ extern "C" int mcosb_create(mcosb_ctx** out, int device, int n_assets, int n_obs
     size_t n = (size_t)n_assets;
     if (cudaMalloc(&ctx->d_mu, n * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&ctx->d_cov, n * n * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_chol, n * n * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_chol, n * n * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_hrp_slow, sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_hrp_slow, 0, sizeof(int)) != cudaSuccess) {
         mcosb_destroy(ctx);
         return MCOSB_ERR_CUDA;
     }
@@ -42,6 +43,7 @@ extern "C" int mcosb_destroy(mcosb_ctx* ctx) {
     if (ctx->d_mu) cudaFree(ctx->d_mu);
     if (ctx->d_cov) cudaFree(ctx->d_cov);
     if (ctx->d_chol) cudaFree(ctx->d_chol);
+    if (ctx->d_hrp_slow) cudaFree(ctx->d_hrp_slow);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MCOSB_OK;

@@ -14,7 +14,7 @@
 enum ScratchSlot {
     SL_STAGE_IN0 = 0, SL_STAGE_IN1, SL_STAGE_IN2, SL_STAGE_IN3,
     SL_STAGE_OUT0, SL_STAGE_OUT1, SL_STAGE_OUT2, SL_STAGE_OUT3, SL_STAGE_OUT4,
-    SL_Z, SL_X, SL_MUHAT, SL_COV, SL_COLMEAN, SL_LWPART, SL_LWSTAT, SL_LWCOEF,
+    SL_Z, SL_X, SL_MUHAT, SL_COV, SL_COLMEAN, SL_LWPART, SL_LWSTAT, SL_LWCOEF, SL_HRP_RN, SL_HRP_FLAG,
     SL_DN_A, SL_DN_SIGMA, SL_DN_D, SL_DN_E, SL_DN_TAU, SL_DN_LAM, SL_DN_VAR, SL_DN_NF, SL_DN_VEC, SL_DN_WORK,
     SL_MK_L, SL_MK_W, SL_MK_ITERS,
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
@@ -56,6 +56,7 @@ enum KernelId {
     MK_SY2SB,
     MK_SB2ST,
     MK_Q2BACK,
+    MK_HRP_GRAM,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -90,7 +91,8 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "risk_parity",
     "sy2sb",
     "sb2st",
-    "q2back"
+    "q2back",
+    "hrp_gram"
 };
 
 struct mcosb_ctx {
@@ -112,6 +114,8 @@ struct mcosb_ctx {
     int num_sms = MCOSB_SMS;
     std::string ideal_key;  // optimizer list whose ideal allocations (on the current truth) sit in SL_IDEAL
     size_t mem_budget = 0;  // free HBM + context-held scratch at the first mcosb_run (wave sizing)
+    int hrp_mode = 0;    // 0 fast MST + exact fallback, 1 exact distances only, 2 fast with every simulation sent to the fallback
+    int* d_hrp_slow = nullptr;   // [1] simulations that took the exact fallback since the counter was last read
     int eig_method = 0;  // 0 auto, 1 one-stage Householder (tridiag / tridiag2), 2 two-stage (sy2sb + sb2st)
     // per-kernel timing (mcosb_set_profiling): one event after every launch; a kernel's time is the gap to the
     // previous event on the stream

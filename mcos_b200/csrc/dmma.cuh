@@ -52,6 +52,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// Lower-triangle tile p -> (I, J), I >= J
+__device__ __forceinline__ void dm_tile_ij(int p, int& I, int& J) {
+    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= p) ++i;
+    while (i * (i + 1) / 2 > p) --i;
+    I = i;
+    J = p - i * (i + 1) / 2;
+}
+
 // One BK-deep slab of MMAs for this warp.  KMAJOR: tile element (mn, k) lives at tile[k * ld + mn]; otherwise at
 // tile[mn * ld + k].  acc[mb][nb][2] follows the m8n8k4 C layout: row = lane/4, cols = 2*(lane%4) + {0,1}.
 // CENTER: subtract per-column offsets (amean[mb], bmean[nb]) from the fragments as they are loaded -- the SYRK's

@@ -8,12 +8,21 @@
 //                      edges, union-find relabelling (scipy mst_single_linkage + label), depth-first leaf order with the
 //                      column-0 child first (optimizer.py:235-249), level-synchronous recursive bisection
 //                      (optimizer.py:256-279).  Weights are returned in POSITION order, as the reference does.
+//
+// Fast path (default): only the MERGE ORDER and the N - 1 merge heights have to be scipy's bits, not all N^2 / 2
+// distances.  hrp_gram_kernel forms approximate squared distances n_i + n_j - 2 D_i . D_j on the FP64 tensor cores
+// (N^3 flop instead of 1.5 N^3 non-fused instructions); Prim runs on them and refuses to decide whenever two candidates
+// are closer than twice a rigorous bound of the approximation error (then the simulation is flagged and redone with the
+// exact distance matrix, bit for bit the old path); the heights of the accepted edges are recomputed with scipy's
+// arithmetic.  Unflagged simulations therefore produce exactly the exact path's linkage.
 #include "common.cuh"
+#include "dmma.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // grid = (ceil(N/32), S), 4 rows per warp; the square roots of the diagonal are taken once per CTA (shared memory).
 // (1 - r) / 2 is an exact halving, so the multiplication by 0.5 rounds like numpy's division.
-__global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D) {
+__global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D,
+                                                       double* __restrict__ rn) {
     extern __shared__ double sg[];   // [N]
     const int s = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -25,11 +34,18 @@ __global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict_
         const int row = blockIdx.x * 32 + wid * 4 + q;
         if (row >= N) return;
         const double si = sg[row];
+        double nrm = 0.0;
         for (int j = lane; j < N; j += 32) {
             double r = __ddiv_rn(c[(size_t)row * N + j], __dmul_rn(si, sg[j]));
             r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
             double v = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
-            d[(size_t)row * N + j] = (j == row) ? 0.0 : v;
+            v = (j == row) ? 0.0 : v;
+            d[(size_t)row * N + j] = v;
+            nrm = fma(v, v, nrm);
+        }
+        if (rn) {                       // squared row norms for the Gram form of the distances (fast path)
+            nrm = warp_sum(nrm);
+            if (lane == 0) rn[(size_t)s * N + row] = nrm;
         }
     }
 }
@@ -44,10 +60,11 @@ __global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict_
 #define EU_LD (EU_T + 2)
 
 __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restrict__ Dall, int N,
-                                                         double* __restrict__ Eall) {
+                                                         double* __restrict__ Eall, const int* __restrict__ only) {
     __shared__ double Si[EU_K][EU_LD];
     __shared__ double Sj[EU_K][EU_LD];
     const int s = blockIdx.y;
+    if (only && !only[s]) return;      // fallback pass: flagged simulations only
     int I = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
     while ((I + 1) * (I + 2) / 2 <= (int)blockIdx.x) ++I;
     while (I * (I + 1) / 2 > (int)blockIdx.x) --I;
@@ -115,12 +132,107 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Fast path: E2[i][j] ~ |D_i - D_j|^2 = n_i + n_j - 2 D_i . D_j with the Gram matrix on the FP64 tensor cores.
+// grid = (lower 128 x 128 tiles, S); both operands are row tiles of D ([row][k] in shared memory, as the TRMM's).
+// |E2 - exact| <= 2 g (n_i + n_j), g = N * 2^-53 (rounding of the N-term dot products and norms); hrp_tree_kernel<true>
+// works with four times that.  Mirrored write: Prim reads rows.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(DM_THREADS, 1)
+hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnall, int N, double* __restrict__ E2all) {
+    extern __shared__ double sm[];
+    const int s = blockIdx.y;
+    int I, J;
+    dm_tile_ij(blockIdx.x, I, J);
+    const bool diag = (I == J);
+    const double* D = Dall + (size_t)s * N * N;
+    const double* rn = rnall + (size_t)s * N;
+    double* E2 = E2all + (size_t)s * N * N;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
+    constexpr int LW = VEC ? 2 : 1, LRS = DM_THREADS * LW / DM_BK;
+    const int lk = (tid % (DM_BK / LW)) * LW, lr = tid / (DM_BK / LW);
+
+    double acc[DM_MB][DM_NB][2];
+#pragma unroll
+    for (int a = 0; a < DM_MB; ++a)
+#pragma unroll
+        for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    auto issue = [&](int kt, int buf) {
+        double* At = sm + (size_t)buf * 2 * DM_TILE_MMAJOR;
+        double* Bt = At + DM_TILE_MMAJOR;
+        const int k = kt * DM_BK + lk;
+        const bool kok = k < N;
+#pragma unroll
+        for (int r = 0; r < DM_BM / LRS; ++r) {
+            const int row = lr + LRS * r;
+            const int ia = I * DM_BM + row, ib = J * DM_BN + row;
+            const bool aok = kok && ia < N, bok = kok && ib < N;
+            if (VEC) {
+                cp_async16(&At[row * DM_LD_MMAJOR + lk], D + (aok ? (size_t)ia * N + k : 0), aok);
+                if (!diag) cp_async16(&Bt[row * DM_LD_MMAJOR + lk], D + (bok ? (size_t)ib * N + k : 0), bok);
+            } else {
+                cp_async8(&At[row * DM_LD_MMAJOR + lk], D + (aok ? (size_t)ia * N + k : 0), aok);
+                if (!diag) cp_async8(&Bt[row * DM_LD_MMAJOR + lk], D + (bok ? (size_t)ib * N + k : 0), bok);
+            }
+        }
+    };
+    const int nkt = (N + DM_BK - 1) / DM_BK;
+#pragma unroll
+    for (int st = 0; st < DM_STAGES - 1; ++st) {
+        if (st < nkt) issue(st, st);
+        cp_async_commit();
+    }
+    // diagonal tile: the warps whose 64 x 32 block lies entirely above the diagonal have nothing to do
+    const bool idle = diag && (wn0 > wm0 + DM_WM - 1);
+    for (int kt = 0; kt < nkt; ++kt) {
+        cp_async_wait<DM_STAGES - 2>();
+        __syncthreads();
+        const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_MMAJOR;
+        const double* Bt = diag ? At : At + DM_TILE_MMAJOR;
+        auto next = [&] {
+            if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
+            cp_async_commit();
+        };
+        if (!idle) dmma_slab<false, false, false>(At, Bt, wm0, wn0, lane, acc, next);
+        else next();
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int mb = 0; mb < DM_MB; ++mb) {
+        const int row = I * DM_BM + wm0 + mb * 8 + g;
+        const double nr = (row < N) ? rn[row] : 0.0;
+#pragma unroll
+        for (int nb = 0; nb < DM_NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = J * DM_BN + wn0 + nb * 8 + 2 * t4 + e;
+                if (row < N && col < N && col <= row) {
+                    double v = fma(-2.0, acc[mb][nb][e], nr + rn[col]);
+                    v = (col == row || v < 0.0) ? 0.0 : v;     // NaN passes through and sends the simulation to the fallback
+                    E2[(size_t)row * N + col] = v;
+                    E2[(size_t)col * N + row] = v;
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 #define TR_THREADS 256
 
+// FAST: Eall holds hrp_gram_kernel's approximate SQUARED distances; decisions closer than the error bound flag the
+// simulation in slow[] (and end the CTA); merge heights are recomputed from D with scipy's arithmetic.
+// !FAST: Eall holds exact distances (hrp_euclid_kernel); with `only`, just the simulations flagged there.
+template <bool FAST>
 __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __restrict__ Eall,
                                                               const double* __restrict__ cov_all, int N,
                                                               double* __restrict__ w_all, int* __restrict__ order_all,
-                                                              double* __restrict__ link_all, int* __restrict__ status) {
+                                                              double* __restrict__ link_all, int* __restrict__ status,
+                                                              const double* __restrict__ Dall,
+                                                              const double* __restrict__ rnall, int* __restrict__ slow,
+                                                              const int* __restrict__ only, int force_slow,
+                                                              int* __restrict__ slow_count) {
     extern __shared__ double sm[];
     // doubles
     double* best = sm;              // [N]   Prim: distance to the tree;  later: position weights
@@ -139,15 +251,38 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
     int* segB = segA + N + 1;       // [N+1]
     int* merged = segB + N + 1;     // [N]
     int* ired = merged + N;         // [32]
+    int* bestx = ired + 32;         // [N]   FAST: the tree node that realises best[i]
     __shared__ int s_x;
+    __shared__ double red2[32];
 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NW = TR_THREADS / 32;
     const double* E = Eall + (size_t)s * N * N;
+    if (!FAST && only && !only[s]) return;
 
     if (N == 1) {
-        if (tid == 0) order_all[s] = 0;
+        if (tid == 0) {
+            order_all[s] = 0;
+            if (FAST && slow) slow[s] = 0;
+        }
         return;
+    }
+    // FAST: decisions need a gap of 3 delta, delta = 16 N u rmax being twice the worst-case bound on |approximate -
+    // scipy's| squared distance (hrp_gram_kernel); the third delta keeps the square roots scipy compares distinct
+    double delta2 = 0.0;
+    int amb = 0;
+    if (FAST) {
+        double rmax = 0.0;
+        for (int i = tid; i < N; i += TR_THREADS) rmax = fmax(rmax, rnall[(size_t)s * N + i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        if (lane == 0) red2[wid] = rmax;
+        __syncthreads();
+        rmax = red2[0];
+        for (int q = 1; q < NW; ++q) rmax = fmax(rmax, red2[q]);
+        delta2 = 3.0 * (16.0 * (double)N * 1.1102230246251565e-16 * rmax);
+        if (!(rmax == rmax) || !(rmax < INFINITY)) amb = 1;
+        __syncthreads();
     }
     // ---- Prim's MST from node 0 (scipy _hierarchy.mst_single_linkage) -------------------------------------------------
     for (int i = tid; i < N; i += TR_THREADS) { best[i] = INFINITY; merged[i] = 0; }
@@ -157,29 +292,56 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
         if (tid == 0) merged[x] = 1;
         __syncthreads();
         const double* row = E + (size_t)x * N;
-        double mv = INFINITY;
+        double mv = INFINITY, m2 = INFINITY;     // smallest and (FAST) second smallest candidate
         int mi = N;
         for (int i = tid; i < N; i += TR_THREADS) {
             if (!merged[i]) {
                 double dd = row[i];
                 double b = best[i];
-                if (b > dd) { b = dd; best[i] = b; }
-                if (b < mv) { mv = b; mi = i; }
+                if (FAST) {
+                    if (!(dd == dd)) amb = 1;
+                    if (b > dd) {
+                        if (b - dd <= delta2) amb = 1;     // two tree nodes (nearly) equally close to i
+                        b = dd; best[i] = b; bestx[i] = x;
+                    } else if (dd - b <= delta2) {
+                        amb = 1;
+                    }
+                    if (b < mv) { m2 = mv; mv = b; mi = i; }
+                    else if (b < m2) m2 = b;
+                } else {
+                    if (b > dd) { b = dd; best[i] = b; }
+                    if (b < mv) { mv = b; mi = i; }
+                }
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double ov = __shfl_xor_sync(0xffffffffu, mv, o);
             int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-            if (ov < mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
+            if (FAST) {
+                const double o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+                const bool take = ov < mv || (ov == mv && oi < mi);
+                m2 = fmin(fmin(m2, o2), take ? mv : ov);
+                if (take) { mv = ov; mi = oi; }
+            } else if (ov < mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
         }
-        if (lane == 0) { red[wid] = mv; ired[wid] = mi; }
+        if (lane == 0) { red[wid] = mv; ired[wid] = mi; if (FAST) red2[wid] = m2; }
         __syncthreads();
         if (tid == 0) {
             double bv = red[0];
             int bi = ired[0];
-            for (int q = 1; q < NW; ++q)
-                if (red[q] < bv || (red[q] == bv && ired[q] < bi)) { bv = red[q]; bi = ired[q]; }
+            if (FAST) {
+                double b2 = red2[0];
+                for (int q = 1; q < NW; ++q) {
+                    const bool take = red[q] < bv || (red[q] == bv && ired[q] < bi);
+                    b2 = fmin(fmin(b2, red2[q]), take ? bv : red[q]);
+                    if (take) { bv = red[q]; bi = ired[q]; }
+                }
+                if (!(b2 - bv > delta2)) amb = 1;    // the runner-up is within the error bound (or nothing finite is left)
+            } else {
+                for (int q = 1; q < NW; ++q)
+                    if (red[q] < bv || (red[q] == bv && ired[q] < bi)) { bv = red[q]; bi = ired[q]; }
+            }
             if (bi >= N) {  // only NaN/inf distances left: take the lowest unmerged index
                 for (int i = 0; i < N; ++i)
                     if (!merged[i] && i != x) { bi = i; break; }
@@ -190,8 +352,31 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
         __syncthreads();
         x = s_x;
     }
-    // ---- stable sort of the N-1 edges by length (rank sort; equal keys keep discovery order) ---------------------------
     const int M = N - 1;
+    if (FAST) {
+        const int flagged = __syncthreads_or(amb | force_slow);
+        if (tid == 0) {
+            slow[s] = flagged;
+            if (flagged) atomicAdd(slow_count, 1);
+        }
+        if (flagged) return;                    // redone by hrp_euclid_kernel + hrp_tree_kernel<false>
+        // merge heights with scipy's arithmetic: sequential over k, separate subtract / multiply / add, then sqrt;
+        // D[y] of mst_single_linkage is the distance to the tree node that realised the minimum
+        const double* D = Dall + (size_t)s * N * N;
+        for (int k = tid; k < M; k += TR_THREADS) {
+            const int b = eb[k], a = bestx[b];
+            const double* ra = D + (size_t)max(a, b) * N;
+            const double* rb = D + (size_t)min(a, b) * N;
+            double acc = 0.0;
+            for (int kk = 0; kk < N; ++kk) {
+                const double df = __dsub_rn(ra[kk], rb[kk]);
+                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+            edist[k] = sqrt(acc);
+        }
+        __syncthreads();
+    }
+    // ---- stable sort of the N-1 edges by length (rank sort; equal keys keep discovery order) ---------------------------
     for (int k = tid; k < M; k += TR_THREADS) {
         const double dk = edist[k];
         int rank = 0;
@@ -365,35 +550,79 @@ __global__ void __launch_bounds__(BS_THREADS) hrp_bisect_kernel(const double* __
 // Euclidean distances between the rows of D for S matrices (also used by NCO's silhouettes); the caller accounts for it.
 void mcosb_launch_euclid(mcosb_ctx* ctx, int S, const double* D, double* E) {
     const int nt = (ctx->N + EU_T - 1) / EU_T;
-    hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, ctx->N, E);
+    hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, ctx->N, E, nullptr);
 }
 
 int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* dorder, double* dlink, int* dstatus) {
     if (S == 0) return MCOSB_OK;
     const int N = ctx->N;
     const size_t n = (size_t)N;
-    double *D, *E;
+    const bool fast = ctx->hrp_mode != 1;
+    double *D, *E, *rn = nullptr;
+    int* slow = nullptr;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_WORK, (size_t)S * n * n, &D));
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_E, (size_t)S * n * n, &E));
-    hrp_dist_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, D);
+    if (fast) {
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_RN, (size_t)S * n, &rn));
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_FLAG, (size_t)S, &slow));
+    }
+    hrp_dist_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, D, rn);
     MCOSB_LAUNCHED(ctx, MK_HRP_DIST);
-    const int nt = (N + EU_T - 1) / EU_T;
-    hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, N, E);
-    MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
     int* order = dorder;
     if (!order) MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_ORDER, (size_t)S * n, &order));
-    size_t smem = (3 * n + 32) * sizeof(double) + (4 * n + 4 * n + n + 2 * (n + 1) + n + 32) * sizeof(int);
+    size_t smem = (3 * n + 32) * sizeof(double) + (4 * n + 4 * n + n + 2 * (n + 1) + n + 32 + n) * sizeof(int);
     if (smem > (size_t)ctx->smem_optin) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for hrp_tree_kernel");
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hrp_tree_kernel<<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus);
+    const int nt = (N + EU_T - 1) / EU_T;
+    if (fast) {
+        // approximate squared distances on the tensor cores, Prim with guarded decisions, exact merge heights
+        const int ng = (N + DM_BM - 1) / DM_BM;
+        const size_t smem_g = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
+        if (N % 2 == 0 && (uintptr_t)D % 16 == 0) {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            hrp_gram_kernel<true><<<dim3(ng * (ng + 1) / 2, S), DM_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
+        } else {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            hrp_gram_kernel<false><<<dim3(ng * (ng + 1) / 2, S), DM_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
+        }
+        MCOSB_LAUNCHED(ctx, MK_HRP_GRAM);
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hrp_tree_kernel<true><<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus, D, rn, slow, nullptr,
+                                                                   ctx->hrp_mode == 2 ? 1 : 0, ctx->d_hrp_slow);
+        MCOSB_LAUNCHED(ctx, MK_HRP_TREE);
+    }
+    // exact distances (bit-identical to scipy's pdist): every simulation, or only those the fast pass flagged
+    hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, N, E, slow);
+    MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hrp_tree_kernel<false><<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus, D, rn, nullptr, slow, 0,
+                                                                nullptr);
     MCOSB_LAUNCHED(ctx, MK_HRP_TREE);
-    double* P = D;  // the distance matrix is dead once E exists: reuse its buffer for the permuted covariance
+    double* P = D;  // the distance matrix is dead once the trees exist: reuse its buffer for the permuted covariance
     hrp_permute_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, order, N, P);
     MCOSB_LAUNCHED(ctx, MK_HRP_PERMUTE);
     size_t smem_b = (3 * n + 32) * sizeof(double) + (2 * (n + 1)) * sizeof(int);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     hrp_bisect_kernel<<<S, BS_THREADS, smem_b, ctx->stream>>>(P, N, dw, dstatus);
     MCOSB_LAUNCHED(ctx, MK_HRP_BISECT);
+    return MCOSB_OK;
+}
+
+// 0 = fast (tensor-core distances, guarded Prim, exact fallback for flagged simulations), 1 = exact distances for every
+// simulation, 2 = fast pass with every simulation sent to the fallback (exercises the gating; results as mode 1)
+extern "C" int mcosb_set_hrp_mode(mcosb_ctx* ctx, int mode) {
+    MCOSB_CHECK_CTX(ctx);
+    if (mode < 0 || mode > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "hrp mode must be 0, 1 or 2");
+    ctx->hrp_mode = mode;
+    return MCOSB_OK;
+}
+
+// Number of simulations the fast pass handed to the exact fallback since the last call (synchronises the stream).
+extern "C" int mcosb_hrp_fallback_count(mcosb_ctx* ctx, int* count) {
+    MCOSB_CHECK_CTX(ctx);
+    if (!count) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_hrp_fallback_count");
+    MCOSB_CUDA(ctx, cudaMemcpyAsync(count, ctx->d_hrp_slow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MCOSB_CUDA(ctx, cudaMemsetAsync(ctx->d_hrp_slow, 0, sizeof(int), ctx->stream));
+    MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MCOSB_OK;
 }
 

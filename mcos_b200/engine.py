@@ -146,6 +146,17 @@ class Engine:
         self._check(self.lib.mcosb_denoise(self.h, s, pc, t, float(bandwidth), pe, pv, pn, ps))
         return kc, {"eigvals": eig, "var": var, "n_facts": nf, "status": st}
 
+    def set_hrp_mode(self, mode: int):
+        """0 = tensor-core distances + guarded Prim + exact fallback (default), 1 = exact distances for every simulation,
+        2 = fast pass with every simulation sent to the fallback (test aid)."""
+        self._check(self.lib.mcosb_set_hrp_mode(self.h, int(mode)))
+
+    def hrp_fallback_count(self) -> int:
+        """Simulations that took HRP's exact fallback since the last call."""
+        c = ctypes.c_int(0)
+        self._check(self.lib.mcosb_hrp_fallback_count(self.h, ctypes.byref(c)))
+        return c.value
+
     def set_eig_method(self, method: int):
         """0 = automatic, 1 = one-stage Householder tridiagonalisation, 2 = two-stage (band reduction + bulge chasing)."""
         self._check(self.lib.mcosb_set_eig_method(self.h, int(method)))

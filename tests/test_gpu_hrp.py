@@ -75,3 +75,47 @@ def test_hrp_exact_ties():
     eng = Engine(30, 50)
     w, info = eng.hrp(cov[None])
     _check(cov, w, info, 0)
+
+
+def test_hrp_fast_path_equals_exact_path_bit_for_bit():
+    """Fast path (tensor-core distances + guarded Prim + exact merge heights, mode 0) against exact distances for every
+    simulation (mode 1) and against the fast pass with every simulation forced through the fallback (mode 2): identical
+    linkage, order and weights, and on sampled covariances almost no simulation needs the fallback."""
+    for n, t, nsim in ((500, 1000, 96), (100, 200, 300), (37, 80, 200), (129, 300, 64)):
+        rng = np.random.RandomState(n + 7)
+        if n % 10 == 0:
+            mu, cov = block_diagonal_truth(n)
+        else:
+            a = rng.standard_normal((n, 2 * n + 1))
+            cov = a @ a.T / (2 * n + 1) * 0.01
+            mu = np.zeros(n)
+        eng = Engine(n, t, seed=5)
+        eng.set_truth(mu, cov)
+        x = eng.sample(nsim)
+        _, covs, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
+        res = {}
+        for mode in (0, 1, 2):
+            eng.set_hrp_mode(mode)
+            eng.hrp_fallback_count()
+            w, info = eng.hrp(covs)
+            res[mode] = (w, info, eng.hrp_fallback_count())
+        eng.set_hrp_mode(0)
+        assert res[1][2] == 0 and res[2][2] == nsim
+        assert res[0][2] <= max(1, nsim // 20), f"{res[0][2]} of {nsim} simulations took the fallback at n={n}"
+        for mode in (0, 2):
+            assert np.array_equal(res[mode][1]["order"], res[1][1]["order"])
+            assert np.array_equal(res[mode][1]["linkage"], res[1][1]["linkage"])
+            assert np.array_equal(res[mode][0], res[1][0])
+            assert (res[mode][1]["status"] == 0).all()
+        _check(covs[0], res[0][0], res[0][1], 0)
+
+
+def test_hrp_ties_take_the_fallback():
+    """Exact ties (the true block-diagonal covariance) are inside the error bound by definition: the fast pass must hand
+    them to the exact path rather than decide."""
+    mu, cov = block_diagonal_truth(100)
+    eng = Engine(100, 10)
+    eng.hrp_fallback_count()
+    w, info = eng.hrp(np.stack([cov, cov]))
+    assert eng.hrp_fallback_count() == 2
+    _check(cov, w, info, 1)
