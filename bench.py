@@ -246,6 +246,7 @@ def run_native(args):
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count
+    eng.hrp_fallback_count()           # reset: count the exact-fallback simulations of the timed steps only
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -257,6 +258,7 @@ def run_native(args):
     ms_local = e0.elapsed_time(e1)
     launches = eng.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
+    hrp_fallback = eng.hrp_fallback_count()
     ktimes = eng.kernel_times()
     stage_ms = eng.last_stage_ms()
     eng.set_profiling(False)
@@ -366,7 +368,8 @@ def run_native(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "stage_ms_last_step": {k: round(v, 3) for k, v in stage_ms.items()},
-            "kernels": table, "status_nonzero_last_step": status_bad, "nan_fraction_last_step": nan_frac,
+            "kernels": table, "hrp_exact_fallback_sims": hrp_fallback, "hrp_sims_timed": spp * args.steps,
+            "status_nonzero_last_step": status_bad, "nan_fraction_last_step": nan_frac,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -132,22 +132,25 @@ __device__ __forceinline__ void dmma_slab(const double* __restrict__ As, const d
 // diagonal) only as 10 of their 16 m8n8 blocks.  Warps 0..5 take one full sub-block each, warps 6 and 7 two diagonal
 // sub-blocks each: at most 20 DMMAs per warp and k-step instead of 32.  A and B fragments come from the same tile
 // (k-major).  Sub-tile U of the warp lives in acc[4 U .. 4 U + 3][*]; its means in amean / bmean[4 U .. 4 U + 3].
-template <bool TRI, bool RAGGED, int U>
+template <bool TRI, bool RAGGED, int U, bool KMAJOR = true, bool CENTER = true>
 __device__ __forceinline__ void dmma_kstep_sub(const double* __restrict__ As, int r0, int c0, int lane, int k0,
                                                double (&acc)[DM_MB][DM_NB][2], const double* amean,
                                                const double* bmean, int kvalid) {
     const int g = lane >> 2, t = lane & 3;
     double a[4], b[4];
     const bool live = !RAGGED || (k0 + t < kvalid);
-    const double* row = As + (k0 + t) * DM_LD_KMAJOR + g;
+    const double* base = KMAJOR ? As + (k0 + t) * DM_LD_KMAJOR + g : As + g * DM_LD_MMAJOR + k0 + t;
+    constexpr int RS = KMAJOR ? 1 : DM_LD_MMAJOR;     // stride between consecutive rows / columns of the tile
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) {
-        a[mb] = row[r0 + mb * 8] - amean[4 * U + mb];
+        a[mb] = base[(r0 + mb * 8) * RS];
+        if (CENTER) a[mb] -= amean[4 * U + mb];
         if (RAGGED) a[mb] = live ? a[mb] : 0.0;
     }
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) {
-        b[nb] = row[c0 + nb * 8] - bmean[4 * U + nb];
+        b[nb] = base[(c0 + nb * 8) * RS];
+        if (CENTER) b[nb] -= bmean[4 * U + nb];
         if (RAGGED) b[nb] = live ? b[nb] : 0.0;
     }
 #pragma unroll
@@ -168,22 +171,22 @@ __device__ __forceinline__ void dmma_diag_subtiles(int wid, int& r0a, int& c0a, 
     }
 }
 
-template <class Mid>
+template <bool KMAJOR = true, bool CENTER = true, class Mid>
 __device__ __forceinline__ void dmma_slab_diag(const double* __restrict__ As, int wid, int lane,
-                                               double (&acc)[DM_MB][DM_NB][2], Mid mid, const double* amean,
-                                               const double* bmean, int kvalid) {
+                                               double (&acc)[DM_MB][DM_NB][2], Mid mid, const double* amean = nullptr,
+                                               const double* bmean = nullptr, int kvalid = DM_BK) {
     int r0a, c0a, r0b, c0b;
     dmma_diag_subtiles(wid, r0a, c0a, r0b, c0b);
     auto step = [&](int k0, auto ragged) {
         constexpr bool R = decltype(ragged)::value;
         if (wid < 6) {
-            dmma_kstep_sub<false, R, 0>(As, r0a, c0a, lane, k0, acc, amean, bmean, kvalid);
+            dmma_kstep_sub<false, R, 0, KMAJOR, CENTER>(As, r0a, c0a, lane, k0, acc, amean, bmean, kvalid);
         } else {
-            dmma_kstep_sub<true, R, 0>(As, r0a, c0a, lane, k0, acc, amean, bmean, kvalid);
-            dmma_kstep_sub<true, R, 1>(As, r0b, c0b, lane, k0, acc, amean, bmean, kvalid);
+            dmma_kstep_sub<true, R, 0, KMAJOR, CENTER>(As, r0a, c0a, lane, k0, acc, amean, bmean, kvalid);
+            dmma_kstep_sub<true, R, 1, KMAJOR, CENTER>(As, r0b, c0b, lane, k0, acc, amean, bmean, kvalid);
         }
     };
-    if (kvalid >= DM_BK) {
+    if (!CENTER || kvalid >= DM_BK) {      // without centring the zero fill of a ragged slab contributes nothing
         step(0, std::false_type{});
         mid();
 #pragma unroll

@@ -184,31 +184,32 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
         if (st < nkt) issue(st, st);
         cp_async_commit();
     }
-    // diagonal tile: the warps whose 64 x 32 block lies entirely above the diagonal have nothing to do
-    const bool idle = diag && (wn0 > wm0 + DM_WM - 1);
+    int r0a = 0, c0a = 0, r0b = 0, c0b = 0;     // diagonal tiles: the lower triangle as sub-blocks (dmma_slab_diag)
+    if (diag) dmma_diag_subtiles(wid, r0a, c0a, r0b, c0b);
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
         const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_MMAJOR;
-        const double* Bt = diag ? At : At + DM_TILE_MMAJOR;
         auto next = [&] {
             if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
             cp_async_commit();
         };
-        if (!idle) dmma_slab<false, false, false>(At, Bt, wm0, wn0, lane, acc, next);
-        else next();
+        if (diag) dmma_slab_diag<false, false>(At, wid, lane, acc, next);
+        else dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc, next);
     }
     const int g = lane >> 2, t4 = lane & 3;
+    const bool two = diag && wid >= 6;
 #pragma unroll
     for (int mb = 0; mb < DM_MB; ++mb) {
-        const int row = I * DM_BM + wm0 + mb * 8 + g;
+        // diagonal tiles: accumulator rows 0..3 are sub-tile a, rows 4..7 sub-tile b (warps 6, 7 only)
+        const int row = I * DM_BM + (diag ? (mb < 4 ? r0a + mb * 8 : r0b + (mb - 4) * 8) : wm0 + mb * 8) + g;
         const double nr = (row < N) ? rn[row] : 0.0;
 #pragma unroll
         for (int nb = 0; nb < DM_NB; ++nb)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int col = J * DM_BN + wn0 + nb * 8 + 2 * t4 + e;
-                if (row < N && col < N && col <= row) {
+                const int col = J * DM_BN + (diag ? (mb < 4 ? c0a : c0b) : wn0) + nb * 8 + 2 * t4 + e;
+                if (row < N && col < N && col <= row && (!diag || mb < 4 || two)) {
                     double v = fma(-2.0, acc[mb][nb][e], nr + rn[col]);
                     v = (col == row || v < 0.0) ? 0.0 : v;     // NaN passes through and sends the simulation to the fallback
                     E2[(size_t)row * N + col] = v;
@@ -368,9 +369,20 @@ __global__ void __launch_bounds__(TR_THREADS) hrp_tree_kernel(const double* __re
             const double* ra = D + (size_t)max(a, b) * N;
             const double* rb = D + (size_t)min(a, b) * N;
             double acc = 0.0;
-            for (int kk = 0; kk < N; ++kk) {
-                const double df = __dsub_rn(ra[kk], rb[kk]);
-                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            if ((N & 1) == 0) {                 // rows are 16-byte aligned: half the load instructions (each touches 32 lines)
+                const double2* pa = reinterpret_cast<const double2*>(ra);
+                const double2* pb = reinterpret_cast<const double2*>(rb);
+                for (int kk = 0; kk < N / 2; ++kk) {
+                    const double2 va = pa[kk], vb = pb[kk];
+                    const double d0 = __dsub_rn(va.x, vb.x), d1 = __dsub_rn(va.y, vb.y);
+                    acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+                    acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+                }
+            } else {
+                for (int kk = 0; kk < N; ++kk) {
+                    const double df = __dsub_rn(ra[kk], rb[kk]);
+                    acc = __dadd_rn(acc, __dmul_rn(df, df));
+                }
             }
             edist[k] = sqrt(acc);
         }

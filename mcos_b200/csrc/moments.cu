@@ -139,7 +139,7 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
             if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
             cp_async_commit();
         };
-        if (diag) dmma_slab_diag(At, wid, lane, acc, next, amean, bmean, T - kt * DM_BK);
+        if (diag) dmma_slab_diag<true, true>(At, wid, lane, acc, next, amean, bmean, T - kt * DM_BK);
         else dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, next, amean, bmean, T - kt * DM_BK);
     }
 
