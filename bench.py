@@ -73,7 +73,8 @@ def kernel_models(n, t):
         "hrp_dist": ("hbm", 16.0 * n * n, "B"),
         "hrp_gram": ("tensor", n3, "flop"),                               # lower triangle of D D' on DMMA (fast path)
         "hrp_euclid": ("fp64_nofma", 3.0 * n3 / 2, "instr"),              # sub, mul, add per (i<j, k): exact fallback only
-        "hrp_tree": ("hbm", 8.0 * n * n, "B"),                            # Prim reads every row of E once
+        "hrp_prim": ("hbm", 8.0 * n * n, "B"),                            # Prim reads every row of the squared distances once
+        "hrp_tree": ("hbm", 2 * 8.0 * n * n, "B"),                        # merge heights: two rows of D per edge
         "hrp_permute": ("hbm", 16.0 * n * n, "B"),                        # covariance gathered into quasi-diagonal order
         "hrp_bisect": ("hbm", 16.0 * n * n, "B"),                         # every level reads its diagonal blocks: 2 N^2 total
         "errors": ("hbm", 8.0 * n * n / 8, "B"),                          # true cov shared by 8 simulations per CTA

@@ -14,7 +14,7 @@
 enum ScratchSlot {
     SL_STAGE_IN0 = 0, SL_STAGE_IN1, SL_STAGE_IN2, SL_STAGE_IN3,
     SL_STAGE_OUT0, SL_STAGE_OUT1, SL_STAGE_OUT2, SL_STAGE_OUT3, SL_STAGE_OUT4,
-    SL_Z, SL_X, SL_MUHAT, SL_COV, SL_COLMEAN, SL_LWPART, SL_LWSTAT, SL_LWCOEF, SL_HRP_RN, SL_HRP_FLAG,
+    SL_Z, SL_X, SL_MUHAT, SL_COV, SL_COLMEAN, SL_LWPART, SL_LWSTAT, SL_LWCOEF, SL_HRP_RN, SL_HRP_FLAG, SL_HRP_EDGES,
     SL_DN_A, SL_DN_SIGMA, SL_DN_D, SL_DN_E, SL_DN_TAU, SL_DN_LAM, SL_DN_VAR, SL_DN_NF, SL_DN_VEC, SL_DN_WORK,
     SL_MK_L, SL_MK_W, SL_MK_ITERS,
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
@@ -57,6 +57,7 @@ enum KernelId {
     MK_SB2ST,
     MK_Q2BACK,
     MK_HRP_GRAM,
+    MK_HRP_PRIM,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -92,7 +93,8 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "sy2sb",
     "sb2st",
     "q2back",
-    "hrp_gram"
+    "hrp_gram",
+    "hrp_prim"
 };
 
 struct mcosb_ctx {

@@ -222,10 +222,104 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
 // ---------------------------------------------------------------------------------------------------------------
 #define TR_THREADS 256
 
-// FAST: Eall holds hrp_gram_kernel's approximate SQUARED distances; decisions closer than the error bound flag the
-// simulation in slow[] (and end the CTA); merge heights are recomputed from D with scipy's arithmetic.
-// !FAST: Eall holds exact distances (hrp_euclid_kernel); with `only`, just the simulations flagged there.
-template <bool FAST>
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path, N <= 1024: scipy's Prim on the approximate squares with ONE WARP per simulation.  best[] / bestx[] / the
+// merged set live in registers (lane l owns nodes l, l + 32, ...), the argmin is a shuffle butterfly, there is no shared
+// memory and no barrier, and many simulations are in flight per SM to hide the latency of the row load each step depends
+// on (the block-per-simulation version spent 2.6-3.5 M cycles per simulation here: three barriers and a serial
+// section per step).  Same guarded decisions as hrp_tree_kernel<1>; the first ambiguous one flags the simulation and
+// ends the warp.  edges[s][0][k], [1][k], [2][k] = x, y and the tree node that realises best[y] of step k.
+// ---------------------------------------------------------------------------------------------------------------
+#define PR_WARPS 4
+template <int MAXM>
+__global__ void __launch_bounds__(PR_WARPS * 32) hrp_prim_kernel(const double* __restrict__ E2all,
+                                                                 const double* __restrict__ rnall, int N, int S,
+                                                                 unsigned short* __restrict__ edges,
+                                                                 int* __restrict__ slow, int force_slow,
+                                                                 int* __restrict__ slow_count) {
+    const int s = blockIdx.x * PR_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= S) return;
+    if (N < 2) {
+        if (lane == 0) slow[s] = 0;
+        return;
+    }
+    const double* E2 = E2all + (size_t)s * N * N;
+    unsigned short* eg = edges + (size_t)s * 3 * N;
+    double rmax = 0.0;
+    for (int i = lane; i < N; i += 32) rmax = fmax(rmax, rnall[(size_t)s * N + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    const double delta2 = 3.0 * (16.0 * (double)N * 1.1102230246251565e-16 * rmax);
+    int amb = (!(rmax == rmax) || !(rmax < INFINITY)) ? 1 : force_slow;
+    double best[MAXM];
+    int bx[MAXM];
+    unsigned mergedmask = 0;            // bit m: node lane + 32 m is in the tree (or does not exist)
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        best[m] = INFINITY;
+        bx[m] = 0;
+        if (lane + 32 * m >= N) mergedmask |= 1u << m;
+    }
+    int x = 0;
+    for (int k = 0; k < N - 1 && !amb; ++k) {
+        if ((x & 31) == lane) mergedmask |= 1u << (x >> 5);
+        const double* row = E2 + (size_t)x * N;
+        double mv = INFINITY, m2 = INFINITY;
+        int mi = N;
+        // the whole row first, unconditionally (clamped index): behind the per-node predicate every load would sit in its
+        // own branch and expose its latency, 16 times per step
+        double dv[MAXM];
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) dv[m] = row[min(lane + 32 * m, N - 1)];
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (!((mergedmask >> m) & 1u)) {
+                const double dd = dv[m];
+                double b = best[m];
+                if (!(dd == dd)) amb = 1;
+                if (b > dd) {
+                    if (b - dd <= delta2) amb = 1;     // two tree nodes (nearly) equally close to this node
+                    b = dd; best[m] = b; bx[m] = x;
+                } else if (dd - b <= delta2) {
+                    amb = 1;
+                }
+                if (b < mv) { m2 = mv; mv = b; mi = lane + 32 * m; }
+                else if (b < m2) m2 = b;
+            }
+        }
+        int bxv = 0;                     // bx of this lane's best candidate
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m)
+            if (mi == lane + 32 * m) bxv = bx[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, mv, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, o), ob = __shfl_xor_sync(0xffffffffu, bxv, o);
+            const bool take = ov < mv || (ov == mv && oi < mi);
+            m2 = fmin(fmin(m2, o2), take ? mv : ov);
+            if (take) { mv = ov; mi = oi; bxv = ob; }
+        }
+        amb = __any_sync(0xffffffffu, amb) ? 1 : 0;
+        if (!(m2 - mv > delta2) || mi >= N) amb = 1;   // runner-up within the error bound, or nothing finite left
+        if (lane == 0) {
+            eg[k] = (unsigned short)x;
+            eg[N + k] = (unsigned short)mi;
+            eg[2 * N + k] = (unsigned short)bxv;
+        }
+        x = mi;
+    }
+    if (lane == 0) {
+        slow[s] = amb;
+        if (amb) atomicAdd(slow_count, 1);
+    }
+}
+
+// MODE 1 (FAST): Eall holds hrp_gram_kernel's approximate SQUARED distances; decisions closer than the error bound flag
+// the simulation in slow[] (and end the CTA); merge heights are recomputed from D with scipy's arithmetic.
+// MODE 2 (FAST, N <= 1024): Prim has already run in hrp_prim_kernel (one warp per simulation); its edges come from
+// `edges`, unflagged simulations continue with the merge heights.
+// MODE 0: Eall holds exact distances (hrp_euclid_kernel); with `only`, just the simulations flagged by the fast pass.
+template <int MODE>
 __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* __restrict__ Eall,
                                                               const double* __restrict__ cov_all, int N,
                                                               double* __restrict__ w_all, int* __restrict__ order_all,
@@ -233,7 +327,9 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
                                                               const double* __restrict__ Dall,
                                                               const double* __restrict__ rnall, int* __restrict__ slow,
                                                               const int* __restrict__ only, int force_slow,
-                                                              int* __restrict__ slow_count) {
+                                                              int* __restrict__ slow_count,
+                                                              const unsigned short* __restrict__ edges) {
+    constexpr bool FAST = MODE != 0;
     extern __shared__ double sm[];
     // doubles
     double* best = sm;              // [N]   Prim: distance to the tree;  later: position weights
@@ -268,10 +364,22 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
         }
         return;
     }
+    if (MODE == 2) {
+        // edges (x, y, tree node realising best[y]) of hrp_prim_kernel; flagged simulations never get here
+        if (slow[s]) return;
+        const unsigned short* eg = edges + (size_t)s * 3 * N;
+        for (int k = tid; k < N - 1; k += TR_THREADS) {
+            ea[k] = eg[k];
+            eb[k] = eg[N + k];
+            bestx[eg[N + k]] = eg[2 * N + k];
+        }
+        __syncthreads();
+    }
     // FAST: decisions need a gap of 3 delta, delta = 16 N u rmax being twice the worst-case bound on |approximate -
     // scipy's| squared distance (hrp_gram_kernel); the third delta keeps the square roots scipy compares distinct
     double delta2 = 0.0;
     int amb = 0;
+    if (MODE != 2) {
     if (FAST) {
         double rmax = 0.0;
         for (int i = tid; i < N; i += TR_THREADS) rmax = fmax(rmax, rnall[(size_t)s * N + i]);
@@ -285,6 +393,9 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
         if (!(rmax == rmax) || !(rmax < INFINITY)) amb = 1;
         __syncthreads();
     }
+#ifdef HRP_TIMING
+    long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0;
+#endif
     // ---- Prim's MST from node 0 (scipy _hierarchy.mst_single_linkage) -------------------------------------------------
     for (int i = tid; i < N; i += TR_THREADS) { best[i] = INFINITY; merged[i] = 0; }
     __syncthreads();
@@ -353,14 +464,20 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
         __syncthreads();
         x = s_x;
     }
+    }
     const int M = N - 1;
+#ifdef HRP_TIMING
+    tq1 = clock64();
+#endif
     if (FAST) {
-        const int flagged = __syncthreads_or(amb | force_slow);
-        if (tid == 0) {
-            slow[s] = flagged;
-            if (flagged) atomicAdd(slow_count, 1);
+        if (MODE == 1) {
+            const int flagged = __syncthreads_or(amb | force_slow);
+            if (tid == 0) {
+                slow[s] = flagged;
+                if (flagged) atomicAdd(slow_count, 1);
+            }
+            if (flagged) return;                // redone by hrp_euclid_kernel + hrp_tree_kernel<0>
         }
-        if (flagged) return;                    // redone by hrp_euclid_kernel + hrp_tree_kernel<false>
         // merge heights with scipy's arithmetic: sequential over k, separate subtract / multiply / add, then sqrt;
         // D[y] of mst_single_linkage is the distance to the tree node that realised the minimum
         const double* D = Dall + (size_t)s * N * N;
@@ -388,6 +505,9 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
         }
         __syncthreads();
     }
+#ifdef HRP_TIMING
+    tq2 = clock64();
+#endif
     // ---- stable sort of the N-1 edges by length (rank sort; equal keys keep discovery order) ---------------------------
     for (int k = tid; k < M; k += TR_THREADS) {
         const double dk = edist[k];
@@ -431,6 +551,11 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
         }
     }
     for (int i = tid; i < N; i += TR_THREADS) order_all[(size_t)s * N + i] = order[i];
+#ifdef HRP_TIMING
+    tq3 = clock64();
+    if (tid == 0 && (s == 7 || s == 3000))
+        printf("hrp_tree<%d> sim %d: prim %lld heights %lld sort+label+dfs %lld cycles\n", (int)FAST, s, tq1 - tq0, tq2 - tq1, tq3 - tq2);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -598,17 +723,36 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
             hrp_gram_kernel<false><<<dim3(ng * (ng + 1) / 2, S), DM_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
         }
         MCOSB_LAUNCHED(ctx, MK_HRP_GRAM);
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hrp_tree_kernel<true><<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus, D, rn, slow, nullptr,
-                                                                   ctx->hrp_mode == 2 ? 1 : 0, ctx->d_hrp_slow);
+        const int force = ctx->hrp_mode == 2 ? 1 : 0;
+        if (N <= 1024) {
+            // Prim with one warp per simulation, then heights / sort / labelling with one CTA per simulation
+            unsigned short* edges;
+            MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_EDGES, (size_t)S * 3 * n, &edges));
+            const unsigned gp = (unsigned)((S + PR_WARPS - 1) / PR_WARPS);
+#define PR_LAUNCH(M) hrp_prim_kernel<M><<<gp, PR_WARPS * 32, 0, ctx->stream>>>(E, rn, N, S, edges, slow, force, ctx->d_hrp_slow)
+            if (N <= 128) PR_LAUNCH(4);
+            else if (N <= 256) PR_LAUNCH(8);
+            else if (N <= 512) PR_LAUNCH(16);
+            else if (N <= 768) PR_LAUNCH(24);
+            else PR_LAUNCH(32);
+#undef PR_LAUNCH
+            MCOSB_LAUNCHED(ctx, MK_HRP_PRIM);
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hrp_tree_kernel<2><<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus, D, rn, slow, nullptr,
+                                                                    force, ctx->d_hrp_slow, edges);
+        } else {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hrp_tree_kernel<1><<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus, D, rn, slow, nullptr,
+                                                                    force, ctx->d_hrp_slow, nullptr);
+        }
         MCOSB_LAUNCHED(ctx, MK_HRP_TREE);
     }
     // exact distances (bit-identical to scipy's pdist): every simulation, or only those the fast pass flagged
     hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, N, E, slow);
     MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
-    MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hrp_tree_kernel<false><<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus, D, rn, nullptr, slow, 0,
-                                                                nullptr);
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_tree_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hrp_tree_kernel<0><<<S, TR_THREADS, smem, ctx->stream>>>(E, dcov, N, dw, order, dlink, dstatus, D, rn, nullptr, slow, 0,
+                                                            nullptr, nullptr);
     MCOSB_LAUNCHED(ctx, MK_HRP_TREE);
     double* P = D;  // the distance matrix is dead once the trees exist: reuse its buffer for the permuted covariance
     hrp_permute_kernel<<<dim3((N + 7) / 8, S), 256, 0, ctx->stream>>>(dcov, order, N, P);
