@@ -323,8 +323,9 @@ def run_native(args):
                        "unit": u, "frac": ach / peak}
     tot = sum(v["ms"] for v in table.values()) or 1.0
     # launches that do next to nothing in this plan (the Ledoit-Wolf coefficient kernel: the shrink itself is folded into
-    # the de-noiser's correlation pass) have no meaningful roofline entry
-    table = {k: v for k, v in table.items() if v["ms"] / tot >= 5e-4}
+    # the de-noiser's correlation pass; HRP's exact-distance kernel, which only flagged simulations enter) have no
+    # meaningful roofline entry
+    table = {k: v for k, v in table.items() if v["ms"] / tot >= 2e-3}
     for v in table.values():
         v["share"] = round(v["ms"] / tot, 4)
     top = max(table, key=lambda k: table[k]["ms"])
