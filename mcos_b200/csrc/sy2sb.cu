@@ -145,16 +145,9 @@ sy2sb_kernel(double* Aall, int N, int LD, double* __restrict__ tauall) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const double vi = Vp[k * LD + i], wi = Wp[k * LD + i];
-                        // the panel's own rows of W and V (the same for every thread): 16-byte broadcast loads (LD and j1
-                        // are multiples of 8, so the pairs are aligned)
-                        const double2* wq = reinterpret_cast<const double2*>(Wp + k * LD + j1);
-                        const double2* vq = reinterpret_cast<const double2*>(Vp + k * LD + j1);
 #pragma unroll
-                        for (int c2 = 0; c2 < 4; ++c2) {
-                            const double2 w2 = wq[c2], v2 = vq[c2];
-                            p[r][2 * c2] = fma(-vi, w2.x, fma(-wi, v2.x, p[r][2 * c2]));
-                            p[r][2 * c2 + 1] = fma(-vi, w2.y, fma(-wi, v2.y, p[r][2 * c2 + 1]));
-                        }
+                        for (int c = 0; c < 8; ++c)
+                            p[r][c] = fma(-vi, Wp[k * LD + j1 + c], fma(-wi, Vp[k * LD + j1 + c], p[r][c]));
                     }
                 }
                 if (i < R0 || last) {          // diagonal block of the band (or nothing left to factorise): final
