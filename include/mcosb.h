@@ -118,7 +118,7 @@ int mcosb_hrp(mcosb_ctx* ctx, int S, const double* cov, double* w, int* order, d
  * every comparison guarded by a rigorous error bound, merge heights recomputed with scipy's arithmetic; a simulation
  * with any comparison inside the bound is redone with exact distances, so the linkage is scipy's bit for bit either
  * way.  1: exact distances (scipy's pdist arithmetic) for every simulation.  2: as 0 with every simulation sent to the
- * exact fallback (test aid). */
+ * exact fallback (test aid).  3: as 0 with the variant of the fast path used above 1024 assets (test aid). */
 int mcosb_set_hrp_mode(mcosb_ctx* ctx, int mode);
 
 /* Number of simulations that took the exact fallback since the last call (host int; synchronises the stream). */

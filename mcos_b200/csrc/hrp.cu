@@ -724,7 +724,7 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
         }
         MCOSB_LAUNCHED(ctx, MK_HRP_GRAM);
         const int force = ctx->hrp_mode == 2 ? 1 : 0;
-        if (N <= 1024) {
+        if (N <= 1024 && ctx->hrp_mode != 3) {
             // Prim with one warp per simulation, then heights / sort / labelling with one CTA per simulation
             unsigned short* edges;
             MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_EDGES, (size_t)S * 3 * n, &edges));
@@ -765,10 +765,11 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
 }
 
 // 0 = fast (tensor-core distances, guarded Prim, exact fallback for flagged simulations), 1 = exact distances for every
-// simulation, 2 = fast pass with every simulation sent to the fallback (exercises the gating; results as mode 1)
+// simulation, 2 = fast pass with every simulation sent to the fallback (exercises the gating; results as mode 1),
+// 3 = fast path with Prim inside the per-CTA tree kernel (what n_assets > 1024 uses), for any size (test aid)
 extern "C" int mcosb_set_hrp_mode(mcosb_ctx* ctx, int mode) {
     MCOSB_CHECK_CTX(ctx);
-    if (mode < 0 || mode > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "hrp mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return mcosb_fail(ctx, MCOSB_ERR_ARG, "hrp mode must be 0, 1, 2 or 3");
     ctx->hrp_mode = mode;
     return MCOSB_OK;
 }

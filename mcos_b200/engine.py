@@ -148,7 +148,7 @@ class Engine:
 
     def set_hrp_mode(self, mode: int):
         """0 = tensor-core distances + guarded Prim + exact fallback (default), 1 = exact distances for every simulation,
-        2 = fast pass with every simulation sent to the fallback (test aid)."""
+        2 = fast pass with every simulation sent to the fallback, 3 = the fast-path variant used above 1024 assets (test aids)."""
         self._check(self.lib.mcosb_set_hrp_mode(self.h, int(mode)))
 
     def hrp_fallback_count(self) -> int:

@@ -94,7 +94,7 @@ def test_hrp_fast_path_equals_exact_path_bit_for_bit():
         x = eng.sample(nsim)
         _, covs, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
         res = {}
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             eng.set_hrp_mode(mode)
             eng.hrp_fallback_count()
             w, info = eng.hrp(covs)
@@ -102,7 +102,8 @@ def test_hrp_fast_path_equals_exact_path_bit_for_bit():
         eng.set_hrp_mode(0)
         assert res[1][2] == 0 and res[2][2] == nsim
         assert res[0][2] <= max(1, nsim // 20), f"{res[0][2]} of {nsim} simulations took the fallback at n={n}"
-        for mode in (0, 2):
+        assert res[3][2] == res[0][2]          # mode 3 = the monolithic fast kernel (n_assets > 1024): same decisions
+        for mode in (0, 2, 3):
             assert np.array_equal(res[mode][1]["order"], res[1][1]["order"])
             assert np.array_equal(res[mode][1]["linkage"], res[1][1]["linkage"])
             assert np.array_equal(res[mode][0], res[1][0])
