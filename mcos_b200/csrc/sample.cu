@@ -7,6 +7,8 @@
 //                          pipe and by the 8TN bytes it writes.
 //   trmm_kernel          : X = mu + Z L'  as one (S*T) x N x N FP64 tensor-core GEMM over all simulations at once
 //                          (L is shared), skipping the k-slabs above the diagonal.  Flops 2 * T * N^2 / 2.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dmma.cuh"
 
@@ -147,6 +149,91 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
             }
 }
 
+// The same product with 128 x 64 tiles and 4 warps (2 x 2, each 64 x 32), two CTAs per SM: while one CTA fills its
+// pipeline or writes its tile the other keeps the tensor pipe busy (with one 256-thread CTA per SM about 10 % of the kernel
+// was prologue / epilogue, most of it in the short tiles at the top of the triangle).
+#define T2_THREADS 128
+#define T2_BN 64
+#define T2_STAGE ((DM_BM + T2_BN) * DM_LD_MMAJOR)
+template <bool VEC>
+__global__ void __launch_bounds__(T2_THREADS, 2)
+trmm2_kernel(const double* __restrict__ Z, const double* __restrict__ L, const double* __restrict__ mu, size_t M, int N,
+             double* __restrict__ X) {
+    extern __shared__ double sm[];
+    const int J = blockIdx.x;
+    const size_t m0 = (size_t)blockIdx.y * DM_BM;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int wm0 = (wid >> 1) * DM_WM, wn0 = (wid & 1) * DM_WN;
+    constexpr int LW = VEC ? 2 : 1, LRS = T2_THREADS * LW / DM_BK;   // rows per loader pass
+    const int lk = (tid % (DM_BK / LW)) * LW, lr = tid / (DM_BK / LW);
+
+    double acc[DM_MB][DM_NB][2];
+#pragma unroll
+    for (int a = 0; a < DM_MB; ++a)
+#pragma unroll
+        for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    auto issue = [&](int kt, int buf) {
+        double* At = sm + (size_t)buf * T2_STAGE;
+        double* Bt = At + DM_TILE_MMAJOR;
+        const int k = kt * DM_BK + lk;
+        const bool kok = k < N;
+#pragma unroll
+        for (int r = 0; r < DM_BM / LRS; ++r) {
+            const int row = lr + LRS * r;
+            const size_t m = m0 + row;
+            const bool aok = kok && m < M;
+            if (VEC) cp_async16(&At[row * DM_LD_MMAJOR + lk], Z + (aok ? m * N + k : 0), aok);
+            else cp_async8(&At[row * DM_LD_MMAJOR + lk], Z + (aok ? m * N + k : 0), aok);
+        }
+#pragma unroll
+        for (int r = 0; r < T2_BN / LRS; ++r) {
+            const int row = lr + LRS * r;
+            const int j = J * T2_BN + row;
+            const bool bok = kok && j < N;
+            if (VEC) cp_async16(&Bt[row * DM_LD_MMAJOR + lk], L + (bok ? (size_t)j * N + k : 0), bok);
+            else cp_async8(&Bt[row * DM_LD_MMAJOR + lk], L + (bok ? (size_t)j * N + k : 0), bok);
+        }
+    };
+    const int kend = min(N, (J + 1) * T2_BN);  // L[j][k] = 0 for k > j
+    const int nkt = (kend + DM_BK - 1) / DM_BK;
+#pragma unroll
+    for (int st = 0; st < DM_STAGES - 1; ++st) {
+        if (st < nkt) issue(st, st);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nkt; ++kt) {
+        cp_async_wait<DM_STAGES - 2>();
+        __syncthreads();
+        const double* At = sm + (size_t)(kt % DM_STAGES) * T2_STAGE;
+        auto next = [&] {
+            if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
+            cp_async_commit();
+        };
+        if (kt * DM_BK <= J * T2_BN + wn0 + DM_WN - 1)   // L[j][k] = 0 for k > j: nothing for this warp's columns
+            dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc, next);
+        else
+            next();
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int mb = 0; mb < DM_MB; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < DM_NB; ++nb) {
+            const size_t row = m0 + wm0 + mb * 8 + g;
+            const int col = J * T2_BN + wn0 + nb * 8 + 2 * t4;
+            if (row < M) {
+                if (VEC && col + 1 < N) {
+                    *reinterpret_cast<double2*>(X + row * N + col) =
+                        make_double2(acc[mb][nb][0] + mu[col], acc[mb][nb][1] + mu[col + 1]);
+                } else {
+                    if (col < N) X[row * N + col] = acc[mb][nb][0] + mu[col];
+                    if (col + 1 < N) X[row * N + col + 1] = acc[mb][nb][1] + mu[col + 1];
+                }
+            }
+        }
+}
+
 int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
     if (S == 0) return MCOSB_OK;
@@ -157,17 +244,30 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     int grid = (int)std::min<size_t>((M + 7) / 8, (size_t)ctx->num_sms * 16);   // 8 warps = 8 rows per CTA and pass
     philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
     MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
-    const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
-
     size_t row_tiles = (M + DM_BM - 1) / DM_BM;
     if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");
-    dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
-    if (N % 2 == 0 && (uintptr_t)dZ % 16 == 0 && (uintptr_t)ctx->d_chol % 16 == 0) {
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        trmm_kernel<true><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+    const bool vec = N % 2 == 0 && (uintptr_t)dZ % 16 == 0 && (uintptr_t)ctx->d_chol % 16 == 0 && (uintptr_t)dX % 16 == 0;
+    static const bool one_cta = std::getenv("MCOSB_TRMM_256") != nullptr;   // the 128 x 128 / 256-thread variant (A/B runs)
+    if (one_cta) {
+        const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
+        dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
+        if (vec) {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trmm_kernel<true><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+        } else {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trmm_kernel<false><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+        }
     } else {
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        trmm_kernel<false><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+        const size_t smem = (size_t)DM_STAGES * T2_STAGE * sizeof(double);
+        dim3 g((N + T2_BN - 1) / T2_BN, (unsigned)row_tiles);
+        if (vec) {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trmm2_kernel<true><<<g, T2_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+        } else {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trmm2_kernel<false><<<g, T2_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+        }
     }
     MCOSB_LAUNCHED(ctx, MK_TRMM);
     return MCOSB_OK;
