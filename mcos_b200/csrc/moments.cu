@@ -42,11 +42,15 @@ __device__ __forceinline__ void tile_ij(int p, int& I, int& J) {
     J = p - i * (i + 1) / 2;
 }
 
-// grid = (lower tiles, S).  lwpart[s][tile][2] receives (sum of squares of the scaled entries this tile stands for in
-// the full symmetric matrix, trace contribution).
+// grid = (2 x lower 128 x 128 tiles, S), 128 threads (4 warps as 2 x 2, each 64 x 32), two CTAs per SM so that the
+// prologue / epilogue of one overlaps the main loop of the other.  An off-diagonal tile is split into its two 128 x 64
+// column halves; a diagonal tile into the two warp sets of dmma_slab_diag (sub-blocks of the lower triangle: 4 x 16 and
+// 2 x 16 + 2 x 20 DMMA per k-step).  lwpart[s][cta][2] receives (sum of squares of the scaled entries this CTA stands
+// for in the full symmetric matrix, trace contribution).
 // VEC: 16-byte cp.async (N even and X 16-byte aligned), otherwise 8-byte copies.
+#define SY_THREADS 128
 template <bool VEC>
-__global__ void __launch_bounds__(DM_THREADS, 1)
+__global__ void __launch_bounds__(SY_THREADS, 2)
 syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T, int N, double scale,
             double* __restrict__ cov, double* __restrict__ lwpart) {
     extern __shared__ double sm[];
@@ -56,26 +60,33 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
 #endif
     const int s = blockIdx.y;
     int I, J;
-    tile_ij(blockIdx.x, I, J);
+    tile_ij(blockIdx.x >> 1, I, J);
+    const int half = blockIdx.x & 1;
     const bool diag = (I == J);
     const double* x = X + (size_t)s * T * N;
     const double* mu = mean + (size_t)s * N;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
-    // loader mapping: VEC: column pair fixed, k = lk + 4r; otherwise column fixed, k = lk + 2r
-    constexpr int LW = VEC ? 2 : 1, LKS = DM_THREADS * LW / DM_BM;
+    const int wm0 = (wid >> 1) * DM_WM, wn0 = (wid & 1) * DM_WN;    // off-diagonal: within the 128 x 64 half
+    const int jcol0 = J * DM_BN + half * (DM_BN / 2);                 // first column of this CTA's B operand
+    const int dwid = half * 4 + wid;                                  // diagonal: warp id of dmma_slab_diag's dealing
+    // loader mapping (A: 128 columns, B: 64): VEC: column pair fixed, k = lk + LKS r; otherwise column fixed
+    constexpr int LW = VEC ? 2 : 1, LKS = SY_THREADS * LW / DM_BM;
     const int lcol = (tid % (DM_BM / LW)) * LW, lk = tid / (DM_BM / LW);
-    const int acol = I * DM_BM + lcol, bcol = J * DM_BN + lcol;
-    const bool aok = acol < N, bok = bcol < N;
+    const int acol = I * DM_BM + lcol;
+    const bool aok = acol < N;
     const double* asrc = x + (aok ? acol : 0);
+    constexpr int LKSB = SY_THREADS * LW / (DM_BN / 2);
+    const int lcolb = (tid % (DM_BN / 2 / LW)) * LW, lkb = tid / (DM_BN / 2 / LW);
+    const int bcol = jcol0 + lcolb;
+    const bool bok = bcol < N;
     const double* bsrc = x + (bok ? bcol : 0);
 
     // per-fragment column means (centring happens in registers, the tiles are copied raw).  Diagonal tiles use the
     // sub-tile decomposition of dmma_slab_diag: means of sub-tile U at [4 U .. 4 U + 3]
     double amean[DM_MB], bmean[DM_MB];
     int r0a = 0, c0a = 0, r0b = 0, c0b = 0;
-    if (diag) dmma_diag_subtiles(wid, r0a, c0a, r0b, c0b);
+    if (diag) dmma_diag_subtiles(dwid, r0a, c0a, r0b, c0b);
     {
         const int g = lane >> 2;
 #pragma unroll
@@ -85,7 +96,7 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
         }
 #pragma unroll
         for (int nb = 0; nb < DM_MB; ++nb) {
-            int c = J * DM_BN + (diag ? (nb < 4 ? c0a : c0b - 32) : wn0) + nb * 8 + g;
+            int c = (diag ? J * DM_BN + (nb < 4 ? c0a : c0b - 32) : jcol0 + wn0) + nb * 8 + g;
             bmean[nb] = (c < N && (diag || nb < DM_NB)) ? mu[c] : 0.0;
         }
     }
@@ -107,12 +118,17 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
             const int kk = lk + LKS * r, k = kbase + kk;
             const bool ok = k < T;
             const size_t goff = (size_t)(ok ? k : 0) * N;
-            if (VEC) {
-                cp_async16(&At[kk * DM_LD_KMAJOR + lcol], asrc + goff, ok && aok);
-                if (!diag) cp_async16(&Bt[kk * DM_LD_KMAJOR + lcol], bsrc + goff, ok && bok);
-            } else {
-                cp_async8(&At[kk * DM_LD_KMAJOR + lcol], asrc + goff, ok && aok);
-                if (!diag) cp_async8(&Bt[kk * DM_LD_KMAJOR + lcol], bsrc + goff, ok && bok);
+            if (VEC) cp_async16(&At[kk * DM_LD_KMAJOR + lcol], asrc + goff, ok && aok);
+            else cp_async8(&At[kk * DM_LD_KMAJOR + lcol], asrc + goff, ok && aok);
+        }
+        if (!diag) {
+#pragma unroll
+            for (int r = 0; r < DM_BK / LKSB; ++r) {
+                const int kk = lkb + LKSB * r, k = kbase + kk;
+                const bool ok = k < T;
+                const size_t goff = (size_t)(ok ? k : 0) * N;
+                if (VEC) cp_async16(&Bt[kk * DM_LD_KMAJOR + lcolb], bsrc + goff, ok && bok);
+                else cp_async8(&Bt[kk * DM_LD_KMAJOR + lcolb], bsrc + goff, ok && bok);
             }
         }
     };
@@ -139,7 +155,7 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
             if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
             cp_async_commit();
         };
-        if (diag) dmma_slab_diag<true, true>(At, wid, lane, acc, next, amean, bmean, T - kt * DM_BK);
+        if (diag) dmma_slab_diag<true, true>(At, dwid, lane, acc, next, amean, bmean, T - kt * DM_BK);
         else dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, next, amean, bmean, T - kt * DM_BK);
     }
 
@@ -150,7 +166,7 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
     const int g = lane >> 2, t4 = lane & 3;
     double* c = cov + (size_t)s * N * N;
     double frob = 0.0, tr = 0.0;
-    const bool two = diag && wid >= 6;
+    const bool two = diag && dwid >= 6;
 #pragma unroll
     for (int mb = 0; mb < DM_MB; ++mb)
 #pragma unroll
@@ -159,7 +175,7 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
             for (int e = 0; e < 2; ++e) {
                 // diagonal tiles: accumulator rows 0..3 are sub-tile a, rows 4..7 sub-tile b (warps 6, 7 only)
                 int row = I * DM_BM + (diag ? (mb < 4 ? r0a + mb * 8 : r0b + (mb - 4) * 8) : wm0 + mb * 8) + g;
-                int col = J * DM_BN + (diag ? (mb < 4 ? c0a : c0b) : wn0) + nb * 8 + 2 * t4 + e;
+                int col = (diag ? J * DM_BN + (mb < 4 ? c0a : c0b) : jcol0 + wn0) + nb * 8 + 2 * t4 + e;
                 if (row < N && col < N && col <= row && (!diag || mb < 4 || two)) {
                     double v = acc[mb][nb][e] * scale;
                     c[(size_t)row * N + col] = v;
@@ -182,7 +198,7 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
         }
     }
 #ifdef SYRK_TIMING
-    if (tid == 0 && s == 1 && blockIdx.x < 10)
+    if (tid == 0 && s == 1 && blockIdx.x < 20)
         printf("syrk tile %d (I %d J %d): setup %lld fill %lld mainloop %lld epilogue %lld cycles\n", blockIdx.x, I, J,
                tk1 - tk0, tk2 - tk1, tk3 - tk2, clock64() - tk3);
 #endif
@@ -289,17 +305,17 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
     colmean_kernel<<<gm, CM_COLS * CM_ROWGROUPS, 0, ctx->stream>>>(dX, T, N, dmu);
     MCOSB_LAUNCHED(ctx, MK_COLMEAN);
 
-    const int nt = (N + DM_BM - 1) / DM_BM, ntiles = nt * (nt + 1) / 2;
+    const int nt = (N + DM_BM - 1) / DM_BM, ntiles = 2 * (nt * (nt + 1) / 2);   // two CTAs per 128 x 128 tile
     double* lwpart = nullptr;
     if (lw) MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWPART, (size_t)S * ntiles * 2, &lwpart));
     const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_KMAJOR * sizeof(double);
     const double scale = lw ? 1.0 / T : 1.0 / (T - 1);
     if (N % 2 == 0 && (uintptr_t)dX % 16 == 0) {
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        syrk_kernel<true><<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
+        syrk_kernel<true><<<dim3(ntiles, S), SY_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
     } else {
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        syrk_kernel<false><<<dim3(ntiles, S), DM_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
+        syrk_kernel<false><<<dim3(ntiles, S), SY_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
     }
     MCOSB_LAUNCHED(ctx, MK_SYRK);
 
