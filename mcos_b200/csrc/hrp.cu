@@ -133,24 +133,31 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fast path: E2[i][j] ~ |D_i - D_j|^2 = n_i + n_j - 2 D_i . D_j with the Gram matrix on the FP64 tensor cores.
-// grid = (lower 128 x 128 tiles, S); both operands are row tiles of D ([row][k] in shared memory, as the TRMM's).
+// grid = (2 x lower 128 x 128 tiles, S); both operands are row tiles of D ([row][k] in shared memory, as the TRMM's).
 // |E2 - exact| <= 2 g (n_i + n_j), g = N * 2^-53 (rounding of the N-term dot products and norms); hrp_tree_kernel<true>
 // works with four times that.  Mirrored write: Prim reads rows.
 // ---------------------------------------------------------------------------------------------------------------
+#define GR_THREADS 128
+#define GR_STAGE ((DM_BM + DM_BN / 2) * DM_LD_MMAJOR)   // doubles per pipeline stage: A (128 rows) + B (64 rows)
 template <bool VEC>
-__global__ void __launch_bounds__(DM_THREADS, 1)
+__global__ void __launch_bounds__(GR_THREADS, 2)
 hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnall, int N, double* __restrict__ E2all) {
+    // two CTAs of 4 warps per 128 x 128 tile, as in syrk_kernel: the column halves of an off-diagonal tile, the two warp
+    // sets of the sub-block dealing on a diagonal one
     extern __shared__ double sm[];
     const int s = blockIdx.y;
     int I, J;
-    dm_tile_ij(blockIdx.x, I, J);
+    dm_tile_ij(blockIdx.x >> 1, I, J);
+    const int half = blockIdx.x & 1;
     const bool diag = (I == J);
     const double* D = Dall + (size_t)s * N * N;
     const double* rn = rnall + (size_t)s * N;
     double* E2 = E2all + (size_t)s * N * N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int wm0 = (wid >> 2) * DM_WM, wn0 = (wid & 3) * DM_WN;
-    constexpr int LW = VEC ? 2 : 1, LRS = DM_THREADS * LW / DM_BK;
+    const int wm0 = (wid >> 1) * DM_WM, wn0 = (wid & 1) * DM_WN;
+    const int jrow0 = J * DM_BN + half * (DM_BN / 2);    // first row of D in this CTA's B operand
+    const int dwid = half * 4 + wid;
+    constexpr int LW = VEC ? 2 : 1, LRS = GR_THREADS * LW / DM_BK;
     const int lk = (tid % (DM_BK / LW)) * LW, lr = tid / (DM_BK / LW);
 
     double acc[DM_MB][DM_NB][2];
@@ -160,21 +167,26 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
         for (int b = 0; b < DM_NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     auto issue = [&](int kt, int buf) {
-        double* At = sm + (size_t)buf * 2 * DM_TILE_MMAJOR;
+        double* At = sm + (size_t)buf * GR_STAGE;
         double* Bt = At + DM_TILE_MMAJOR;
         const int k = kt * DM_BK + lk;
         const bool kok = k < N;
 #pragma unroll
         for (int r = 0; r < DM_BM / LRS; ++r) {
             const int row = lr + LRS * r;
-            const int ia = I * DM_BM + row, ib = J * DM_BN + row;
-            const bool aok = kok && ia < N, bok = kok && ib < N;
-            if (VEC) {
-                cp_async16(&At[row * DM_LD_MMAJOR + lk], D + (aok ? (size_t)ia * N + k : 0), aok);
-                if (!diag) cp_async16(&Bt[row * DM_LD_MMAJOR + lk], D + (bok ? (size_t)ib * N + k : 0), bok);
-            } else {
-                cp_async8(&At[row * DM_LD_MMAJOR + lk], D + (aok ? (size_t)ia * N + k : 0), aok);
-                if (!diag) cp_async8(&Bt[row * DM_LD_MMAJOR + lk], D + (bok ? (size_t)ib * N + k : 0), bok);
+            const int ia = I * DM_BM + row;
+            const bool aok = kok && ia < N;
+            if (VEC) cp_async16(&At[row * DM_LD_MMAJOR + lk], D + (aok ? (size_t)ia * N + k : 0), aok);
+            else cp_async8(&At[row * DM_LD_MMAJOR + lk], D + (aok ? (size_t)ia * N + k : 0), aok);
+        }
+        if (!diag) {
+#pragma unroll
+            for (int r = 0; r < DM_BN / 2 / LRS; ++r) {
+                const int row = lr + LRS * r;
+                const int ib = jrow0 + row;
+                const bool bok = kok && ib < N;
+                if (VEC) cp_async16(&Bt[row * DM_LD_MMAJOR + lk], D + (bok ? (size_t)ib * N + k : 0), bok);
+                else cp_async8(&Bt[row * DM_LD_MMAJOR + lk], D + (bok ? (size_t)ib * N + k : 0), bok);
             }
         }
     };
@@ -185,20 +197,20 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
         cp_async_commit();
     }
     int r0a = 0, c0a = 0, r0b = 0, c0b = 0;     // diagonal tiles: the lower triangle as sub-blocks (dmma_slab_diag)
-    if (diag) dmma_diag_subtiles(wid, r0a, c0a, r0b, c0b);
+    if (diag) dmma_diag_subtiles(dwid, r0a, c0a, r0b, c0b);
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
-        const double* At = sm + (size_t)(kt % DM_STAGES) * 2 * DM_TILE_MMAJOR;
+        const double* At = sm + (size_t)(kt % DM_STAGES) * GR_STAGE;
         auto next = [&] {
             if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
             cp_async_commit();
         };
-        if (diag) dmma_slab_diag<false, false>(At, wid, lane, acc, next);
+        if (diag) dmma_slab_diag<false, false>(At, dwid, lane, acc, next);
         else dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc, next);
     }
     const int g = lane >> 2, t4 = lane & 3;
-    const bool two = diag && wid >= 6;
+    const bool two = diag && dwid >= 6;
 #pragma unroll
     for (int mb = 0; mb < DM_MB; ++mb) {
         // diagonal tiles: accumulator rows 0..3 are sub-tile a, rows 4..7 sub-tile b (warps 6, 7 only)
@@ -208,7 +220,7 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
         for (int nb = 0; nb < DM_NB; ++nb)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int col = J * DM_BN + (diag ? (mb < 4 ? c0a : c0b) : wn0) + nb * 8 + 2 * t4 + e;
+                const int col = (diag ? J * DM_BN + (mb < 4 ? c0a : c0b) : jrow0 + wn0) + nb * 8 + 2 * t4 + e;
                 if (row < N && col < N && col <= row && (!diag || mb < 4 || two)) {
                     double v = fma(-2.0, acc[mb][nb][e], nr + rn[col]);
                     v = (col == row || v < 0.0) ? 0.0 : v;     // NaN passes through and sends the simulation to the fallback
@@ -714,13 +726,13 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
     if (fast) {
         // approximate squared distances on the tensor cores, Prim with guarded decisions, exact merge heights
         const int ng = (N + DM_BM - 1) / DM_BM;
-        const size_t smem_g = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
+        const size_t smem_g = (size_t)DM_STAGES * GR_STAGE * sizeof(double);
         if (N % 2 == 0 && (uintptr_t)D % 16 == 0) {
             MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            hrp_gram_kernel<true><<<dim3(ng * (ng + 1) / 2, S), DM_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
+            hrp_gram_kernel<true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
         } else {
             MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            hrp_gram_kernel<false><<<dim3(ng * (ng + 1) / 2, S), DM_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
+            hrp_gram_kernel<false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
         }
         MCOSB_LAUNCHED(ctx, MK_HRP_GRAM);
         const int force = ctx->hrp_mode == 2 ? 1 : 0;
