@@ -64,7 +64,7 @@ def kernel_models(n, t):
         "sb2st": ("fp64", 6.0 * 8 * n * n, "flop"),                       # bulge chasing, 6 N^2 b flop
         "q2back": ("hbm", 8.0 * n * n, "B"),                              # stage-2 reflectors read once per simulation
         "eigvals": ("fp64", 2.0 * 2 * 64 * n * n, "flop"),                # 64 bisection steps x N-step Sturm recurrence
-        "mpfit": ("fp64", 11 * 1000.0 * n * 25, "flop"),                  # ~11 objective passes x 1000 x N exp (~25 flop)
+        "mpfit": ("fp64", 11 * 1000.0 * n * 5, "flop"),                   # ~11 objective passes x 1000 x N kernel terms x 5 flop (recurrence form)
         "eigvec": ("hbm", 3 * 8.0 * n * n, "B"),                          # reflectors read + cov written and rescaled
         "inviter": ("hbm", 8 * 5 * 8.0 * n * 10, "B"),                    # ~8 passes over 5 N-vectors for ~10 eigenvectors
         "backtransform": ("hbm", 8.0 * n * n / 2, "B"),                   # reflectors read once (shared by the vectors via L1/L2)

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __res
 // line search, pgtol 1e-5, factr 1e7), with the analytic derivative df/dv in place of scipy's forward difference.
 // tests/lbfgsb1d_ref.py is the same logic in numpy, checked against scipy iteration for iteration.
 // ---------------------------------------------------------------------------------------------------------------
-#define MP_THREADS 512
+#define MP_THREADS 256
 #define MP_PTS 1000
 
 struct MPCtx {
@@ -409,8 +409,8 @@ struct MPCtx {
 //   g_k = exp(-(x_k - lam)^2 / 2h^2),  g_{k+1} = g_k r_k,  r_{k+1} = r_k c,  c = exp(-dx^2 / h^2),
 // so a thread that owns MP_KB consecutive grid points pays two exp per eigenvalue instead of MP_KB.  Thread layout:
 // MP_IG threads share one block of MP_KB grid points and split the eigenvalues between them (reduced with shuffles).
-// 1000 points = 63 blocks of 16 x 8 eigenvalue groups = 504 active threads.
-#define MP_KB 16
+// 1000 points = 32 blocks of 32 x 8 eigenvalue groups = 256 threads (blocks of 16 with 512 threads paid twice the exps).
+#define MP_KB 32
 #define MP_IG 8
 __device__ void mp_eval(const MPCtx& c, double v, double& f, double& g) {
     const double sq = sqrt(1.0 / c.q);
