@@ -19,6 +19,8 @@
 #include "common.cuh"
 
 #define NC_THREADS 256
+#define NC_THREADS_MAX 512   // nco_cluster_kernel runs with 512 threads from N = 512 (one CTA per SM there anyway)
+#define NCT ((int)blockDim.x)
 #define NC_MAX_ITER 300
 
 __global__ void __launch_bounds__(256) nco_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D) {
@@ -73,7 +75,7 @@ __device__ __forceinline__ double nc_block_sum(double v, NcSm& s) { return block
 // coalesced row read instead of an N-term dot product per point (sklearn evaluates ||x||^2 - 2 x.y + ||y||^2, which agrees
 // to rounding; the clustering is "not bit for bit" anyway, see the header).
 __device__ void nc_dist_to_point(const double* __restrict__ E, int N, int c, double* out) {
-    for (int i = threadIdx.x; i < N; i += NC_THREADS) {
+    for (int i = threadIdx.x; i < N; i += NCT) {
         const double e = E[(size_t)c * N + i];
         out[i] = e * e;
     }
@@ -88,7 +90,7 @@ __device__ void nc_dist_to_point(const double* __restrict__ E, int N, int c, dou
 // picks[t] = smallest i with closest[0] + ... + closest[i] >= vals[t] (N - 1 if none), t < nv.
 __device__ void nc_pick_multi(const double* __restrict__ wgt, int N, const double (&vals)[NC_CG], int nv, NcSm& s) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int chunk = (N + NC_THREADS - 1) / NC_THREADS;   // consecutive points per thread
+    const int chunk = (N + NCT - 1) / NCT;   // consecutive points per thread
     const int i0 = tid * chunk;
     double ls = 0.0;
     for (int e = 0; e < chunk; ++e)
@@ -121,7 +123,7 @@ __device__ void nc_pick_multi(const double* __restrict__ wgt, int N, const doubl
 
 // out[t][i] = squared distance of point i to candidate s.picks[t], t < nv
 __device__ void nc_dist_multi(const double* __restrict__ E, int N, int nv, NcSm& s, double* __restrict__ out) {
-    for (int idx = threadIdx.x; idx < nv * N; idx += NC_THREADS) {
+    for (int idx = threadIdx.x; idx < nv * N; idx += NCT) {
         const int t = idx / N, i = idx - t * N;
         const double e = E[(size_t)s.picks[t] * N + i];
         out[idx] = e * e;
@@ -145,14 +147,14 @@ __device__ void nc_block_sum_multi(double (&v)[NC_CG], NcSm& s) {
 #pragma unroll
     for (int t = 0; t < NC_CG; ++t) {
         double a = 0.0;
-        for (int ww = 0; ww < NC_THREADS / 32; ++ww) a += s.red[ww * NC_CG + t];
+        for (int ww = 0; ww < NCT / 32; ++ww) a += s.red[ww * NC_CG + t];
         v[t] = a;
     }
 }
 
 // E-step: labels[i] = argmin_j (||c_j||^2 - 2 x_i.c_j), lowest j on ties.
 __device__ void nc_assign(const double* __restrict__ X, int N, int k, NcSm& s) {
-    for (int j = threadIdx.x; j < k; j += NC_THREADS) {
+    for (int j = threadIdx.x; j < k; j += NCT) {
         double q = 0.0;
         for (int d = 0; d < N; ++d) q = fma(s.centers[j * N + d], s.centers[j * N + d], q);
         s.cn2[j] = q;
@@ -161,7 +163,7 @@ __device__ void nc_assign(const double* __restrict__ X, int N, int k, NcSm& s) {
     // one thread per (point, centre) pair (only N of the CTA's threads would work with one thread per point); the scores
     // go through s.cnew (free during the E-step), then each point takes the argmin, lowest j on ties
     double* score = s.cnew;
-    for (int p = threadIdx.x; p < N * k; p += NC_THREADS) {
+    for (int p = threadIdx.x; p < N * k; p += NCT) {
         const int i = p % N, j = p / N;
         const double* ca = s.centers + j * N;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -176,7 +178,7 @@ __device__ void nc_assign(const double* __restrict__ X, int N, int k, NcSm& s) {
         score[p] = s.cn2[j] - 2.0 * ((a0 + a1) + (a2 + a3));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += NC_THREADS) {
+    for (int i = threadIdx.x; i < N; i += NCT) {
         double bestv = INFINITY;
         int bestj = 0;
         for (int j = 0; j < k; ++j) {
@@ -188,7 +190,7 @@ __device__ void nc_assign(const double* __restrict__ X, int N, int k, NcSm& s) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* __restrict__ Dall,
+__global__ void __launch_bounds__(NC_THREADS_MAX) nco_cluster_kernel(const double* __restrict__ Dall,
                                                                  const double* __restrict__ Eall, int N, int max_k,
                                                                  const double* __restrict__ uni,  // [max_k+1][ustride]
                                                                  int ustride, int* __restrict__ labels_out,
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
     s.cn2 = s.colmean + N;
     s.shift = s.cn2 + max_k;
     s.red = s.shift + max_k;
-    s.labels = reinterpret_cast<int*>(s.red + 32);
+    s.labels = reinterpret_cast<int*>(s.red + 64);   // red: (warps <= 16) x NC_CG partial sums
     s.lold = s.labels + N;
     s.lbest = s.lold + N;
     s.counts = s.lbest + N;
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
 
     // centring (KMeans.fit subtracts the column means) and tolerance tol = 1e-4 * mean(var(X, axis=0))
     double vsum = 0.0;
-    for (int d = tid; d < N; d += NC_THREADS) {
+    for (int d = tid; d < N; d += NCT) {
         double m = 0.0;
         for (int i = 0; i < N; ++i) m += X[(size_t)i * N + d];
         m /= N;
@@ -247,10 +249,10 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
         // ---- k-means++ ------------------------------------------------------------------------------------------------
         // first centre: RandomState.choice(n, p=1/n) -- data independent, the index comes with the uniform table
         const int first = (int)u[0];
-        for (int d = tid; d < N; d += NC_THREADS) s.centers[d] = X[(size_t)d * N + first] - s.colmean[d];
+        for (int d = tid; d < N; d += NCT) s.centers[d] = X[(size_t)d * N + first] - s.colmean[d];
         nc_dist_to_point(E, N, first, s.closest);
         double pot = 0.0;
-        for (int i = tid; i < N; i += NC_THREADS) pot += s.closest[i];
+        for (int i = tid; i < N; i += NCT) pot += s.closest[i];
         pot = nc_block_sum(pot, s);
         for (int c = 1; c < k; ++c) {
             double best_pot = INFINITY;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
                 nc_pick_multi(s.closest, N, vals, nv, s);
                 nc_dist_multi(E, N, nv, s, s.cand);
                 double cp[NC_CG] = {0.0, 0.0, 0.0, 0.0};
-                for (int i = tid; i < N; i += NC_THREADS) {
+                for (int i = tid; i < N; i += NCT) {
                     const double cl = s.closest[i];
 #pragma unroll
                     for (int t = 0; t < NC_CG; ++t)
@@ -276,17 +278,17 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
                 for (int t = 0; t < NC_CG; ++t)
                     if (t < nv && cp[t] < best_pot) { best_pot = cp[t]; best_id = s.picks[t]; win = t; }  // first minimum
                 if (win >= 0)
-                    for (int i = tid; i < N; i += NC_THREADS) s.bestd[i] = s.cand[win * N + i];
+                    for (int i = tid; i < N; i += NCT) s.bestd[i] = s.cand[win * N + i];
                 __syncthreads();
             }
-            for (int i = tid; i < N; i += NC_THREADS) s.closest[i] = fmin(s.closest[i], s.bestd[i]);
-            for (int d = tid; d < N; d += NC_THREADS) s.centers[c * N + d] = X[(size_t)d * N + best_id] - s.colmean[d];
+            for (int i = tid; i < N; i += NCT) s.closest[i] = fmin(s.closest[i], s.bestd[i]);
+            for (int d = tid; d < N; d += NCT) s.centers[c * N + d] = X[(size_t)d * N + best_id] - s.colmean[d];
             pot = best_pot;
             __syncthreads();
         }
         NC_TICK(1);
         // ---- Lloyd -----------------------------------------------------------------------------------------------------
-        for (int i = tid; i < N; i += NC_THREADS) s.lold[i] = -1;
+        for (int i = tid; i < N; i += NCT) s.lold[i] = -1;
         __syncthreads();
         bool strict = false;
         for (int it = 0; it < NC_MAX_ITER; ++it) {
@@ -296,9 +298,9 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
             ++niter;
 #endif
             // M-step: new centres = mean of the members; empty clusters take the points farthest from their centres
-            for (int j = tid; j < k; j += NC_THREADS) s.counts[j] = 0;
+            for (int j = tid; j < k; j += NCT) s.counts[j] = 0;
             __syncthreads();
-            for (int i = tid; i < N; i += NC_THREADS) atomicAdd(&s.counts[s.labels[i]], 1);
+            for (int i = tid; i < N; i += NCT) atomicAdd(&s.counts[s.labels[i]], 1);
             __syncthreads();
             // points grouped by cluster (stable: thread j collects cluster j in ascending order), so a centre coordinate is a
             // sum over its own members only instead of a predicated sum over all points
@@ -308,13 +310,13 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
                 s.cstart[k] = acc;
             }
             __syncthreads();
-            for (int j = tid; j < k; j += NC_THREADS) {
+            for (int j = tid; j < k; j += NCT) {
                 int pos = s.cstart[j];
                 for (int i = 0; i < N; ++i)
                     if (s.labels[i] == j) s.members[pos++] = i;
             }
             __syncthreads();
-            for (int idx = tid; idx < k * N; idx += NC_THREADS) {
+            for (int idx = tid; idx < k * N; idx += NCT) {
                 const int j = idx / N, d = idx % N;
                 const double cmd = s.colmean[d];
                 const int e1 = s.cstart[j + 1];
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
             __syncthreads();
             if (s_flag > 0) {
                 // _relocate_empty_clusters_dense: distance of each point to its (old) centre, farthest points first
-                for (int i = tid; i < N; i += NC_THREADS) {
+                for (int i = tid; i < N; i += NCT) {
                     double q = 0.0;
                     const int j = s.labels[i];
                     for (int d = 0; d < N; ++d) {
@@ -367,26 +369,26 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
                 }
                 __syncthreads();
             }
-            for (int idx = tid; idx < k * N; idx += NC_THREADS) {
+            for (int idx = tid; idx < k * N; idx += NCT) {
                 const int j = idx / N;
                 if (s.counts[j] > 0) s.cnew[idx] /= s.counts[j];
             }
             __syncthreads();
-            for (int j = tid; j < k; j += NC_THREADS) {
+            for (int j = tid; j < k; j += NCT) {
                 double q = 0.0;
                 for (int d = 0; d < N; ++d) { double t = s.cnew[j * N + d] - s.centers[j * N + d]; q = fma(t, t, q); }
                 s.shift[j] = q;
             }
             __syncthreads();
-            for (int idx = tid; idx < k * N; idx += NC_THREADS) s.centers[idx] = s.cnew[idx];
+            for (int idx = tid; idx < k * N; idx += NCT) s.centers[idx] = s.cnew[idx];
             int diff = 0;
-            for (int i = tid; i < N; i += NC_THREADS) diff |= (s.labels[i] != s.lold[i]);
+            for (int i = tid; i < N; i += NCT) diff |= (s.labels[i] != s.lold[i]);
             const int changed = __syncthreads_or(diff);
             if (!changed) { strict = true; break; }
             double tot = 0.0;
             for (int j = 0; j < k; ++j) tot += s.shift[j];
             if (tot <= tol) break;
-            for (int i = tid; i < N; i += NC_THREADS) s.lold[i] = s.labels[i];
+            for (int i = tid; i < N; i += NCT) s.lold[i] = s.labels[i];
             __syncthreads();
             NC_TICK(3);
         }
@@ -394,12 +396,12 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
         if (!strict) nc_assign(X, N, k, s);
         // ---- silhouette_samples (Euclidean between rows of D) and the quality mean/std --------------------------------
         double* dsum = s.cnew;  // [k][N] sum of distances from point i to the members of cluster j
-        for (int j = tid; j < k; j += NC_THREADS) s.counts[j] = 0;
+        for (int j = tid; j < k; j += NCT) s.counts[j] = 0;
         __syncthreads();
-        for (int i = tid; i < N; i += NC_THREADS) atomicAdd(&s.counts[s.labels[i]], 1);
-        for (int idx = tid; idx < k * N; idx += NC_THREADS) dsum[idx] = 0.0;
+        for (int i = tid; i < N; i += NCT) atomicAdd(&s.counts[s.labels[i]], 1);
+        for (int idx = tid; idx < k * N; idx += NCT) dsum[idx] = 0.0;
         __syncthreads();
-        for (int i = tid; i < N; i += NC_THREADS) {
+        for (int i = tid; i < N; i += NCT) {
             for (int jx = 0; jx < N; ++jx) {
                 if (jx == i) continue;
                 dsum[s.labels[jx] * N + i] += E[(size_t)jx * N + i];
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
         }
         __syncthreads();
         double ssum = 0.0;
-        for (int i = tid; i < N; i += NC_THREADS) {
+        for (int i = tid; i < N; i += NCT) {
             const int li = s.labels[i];
             const int nli = s.counts[li];
             double sv = 0.0;
@@ -424,12 +426,12 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
         }
         const double mean = nc_block_sum(ssum, s) / N;
         double vs = 0.0;
-        for (int i = tid; i < N; i += NC_THREADS) { double t = s.cand[i] - mean; vs = fma(t, t, vs); }
+        for (int i = tid; i < N; i += NCT) { double t = s.cand[i] - mean; vs = fma(t, t, vs); }
         const double sd = sqrt(nc_block_sum(vs, s) / N);
         const double q = mean / sd;
         if (best_q != best_q || q > best_q) {  // optimizer.py:166
             best_q = q;
-            for (int i = tid; i < N; i += NC_THREADS) s.lbest[i] = s.labels[i];
+            for (int i = tid; i < N; i += NCT) s.lbest[i] = s.labels[i];
         }
         __syncthreads();
         NC_TICK(4);
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(NC_THREADS) nco_cluster_kernel(const double* _
     if (tid == 0 && blockIdx.x == 0) printf("nco_cluster cycles: setup %lld kmeans++ %lld assign %lld mstep %lld silhouette %lld; lloyd iterations %d\n", nacc[0], nacc[1], nacc[2], nacc[3], nacc[4], niter);
 #endif
     {
-    for (int i = tid; i < N; i += NC_THREADS) labels_out[(size_t)sim * N + i] = s.lbest[i];
+    for (int i = tid; i < N; i += NCT) labels_out[(size_t)sim * N + i] = s.lbest[i];
     if (tid == 0 && quality_out) quality_out[sim] = best_q;
     }
 }
@@ -620,12 +622,13 @@ int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, 
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_NCO_E, tab.size(), &duni));
         MCOSB_CUDA(ctx, cudaMemcpyAsync(duni, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tab` is a pageable stack-owned buffer
-        size_t smem = (2 * (size_t)max_k * n + 3 * n + 2 * (size_t)max_k + 32) * sizeof(double) +
+        size_t smem = (2 * (size_t)max_k * n + 3 * n + 2 * (size_t)max_k + 64) * sizeof(double) +
                       (4 * n + 2 * (size_t)max_k + 33 + NC_CG) * sizeof(int);
         if (smem > (size_t)ctx->smem_optin)
             return mcosb_fail(ctx, MCOSB_ERR_ARG, "max_num_clusters x n_assets too large for nco_cluster_kernel's shared memory");
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(nco_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nco_cluster_kernel<<<S, NC_THREADS, smem, ctx->stream>>>(D, E, N, max_k, duni, ustride, labels, nullptr);
+        nco_cluster_kernel<<<S, N >= 512 ? NC_THREADS_MAX : NC_THREADS, smem, ctx->stream>>>(D, E, N, max_k, duni, ustride, labels,
+                                                                                         nullptr);
         MCOSB_LAUNCHED(ctx, MK_NCO_CLUSTER);
     }
     double* work;
