@@ -627,7 +627,7 @@ int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, 
         if (smem > (size_t)ctx->smem_optin)
             return mcosb_fail(ctx, MCOSB_ERR_ARG, "max_num_clusters x n_assets too large for nco_cluster_kernel's shared memory");
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(nco_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nco_cluster_kernel<<<S, N >= 512 ? NC_THREADS_MAX : NC_THREADS, smem, ctx->stream>>>(D, E, N, max_k, duni, ustride, labels,
+        nco_cluster_kernel<<<S, N >= 512 ? NC_THREADS_MAX : (N <= 128 ? 128 : NC_THREADS), smem, ctx->stream>>>(D, E, N, max_k, duni, ustride, labels,
                                                                                          nullptr);
         MCOSB_LAUNCHED(ctx, MK_NCO_CLUSTER);
     }
