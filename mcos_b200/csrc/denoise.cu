@@ -240,7 +240,9 @@ __global__ void __launch_bounds__(TD_THREADS) tridiag_kernel(double* __restrict_
 // instructions per step) with exponent rescaling every 8 steps; #sign changes of (p_0..p_N) = #eigenvalues < x.
 // Output lam[N] sorted DESCENDING (the order _get_PCA produces, covariance_transformer.py:106-107).
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef EV_THREADS
 #define EV_THREADS 256
+#endif
 
 // sde[i] = (d_i, e_{i-1}^2), e_{-1} = 0.  Only the recurrence itself (DADD, DMUL, DFMA) runs on the FP64 pipe: the sign
 // changes are tracked on the integer pipe from the high words (one funnel shift per step collects the change bits, one

@@ -232,7 +232,9 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef TR_THREADS
 #define TR_THREADS 256
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fast path, N <= 1024: scipy's Prim on the approximate squares with ONE WARP per simulation.  best[] / bestx[] / the
@@ -592,7 +594,9 @@ __global__ void __launch_bounds__(256) hrp_permute_kernel(const double* __restri
 // Recursive bisection (optimizer.py:256-279), level by level, on the permuted covariance.  One CTA per simulation.
 // Cluster variance of [lo, hi): w = ivp / sum(ivp), ivp_a = 1 / P[a][a];  var = w' P[lo:hi, lo:hi] w.
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef BS_THREADS
 #define BS_THREADS 256
+#endif
 #define BS_BIG 64   // clusters longer than this are reduced by the whole CTA, shorter ones by one warp each
 
 __global__ void __launch_bounds__(BS_THREADS) hrp_bisect_kernel(const double* __restrict__ P_all, int N,
