@@ -406,7 +406,7 @@ int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double
     static int Wsel = -1;
     if (Wsel < 0) {
         const char* e = getenv("MCOSB_SB2ST_W");
-        Wsel = e ? atoi(e) : 4;
+        Wsel = e ? atoi(e) : 5;   // measured at N = 500 (us per matrix): W = 3 8.50, 4 6.89, 5 6.60, 6 7.22, 8 7.26
     }
 #define SB2ST_LAUNCH(W)                                                                                               \
     do {                                                                                                              \
@@ -430,8 +430,11 @@ int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double
         else SB2ST_LAUNCH_MMA(4);
     } else if (Wsel == 1) SB2ST_LAUNCH(1);
     else if (Wsel == 2) SB2ST_LAUNCH(2);
+    else if (Wsel == 3) SB2ST_LAUNCH(3);
+    else if (Wsel == 4) SB2ST_LAUNCH(4);
+    else if (Wsel == 6) SB2ST_LAUNCH(6);
     else if (Wsel == 8) SB2ST_LAUNCH(8);
-    else SB2ST_LAUNCH(4);
+    else SB2ST_LAUNCH(5);
 #undef SB2ST_LAUNCH
 #undef SB2ST_LAUNCH_MMA
     MCOSB_LAUNCHED(ctx, MK_SB2ST);
