@@ -201,7 +201,9 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
 // N / 32 times per simulation instead of N / 8 from L2), each warp owns 4 output rows and a lane walks the columns, so one
 // shared-memory load of v_sj feeds 4 FMAs.  r_i = lbar + sum_s c_s v_si^2 is the diagonal of the clipped matrix.
 #define RC_ROWS 2
+#ifndef RC_CTA_ROWS
 #define RC_CTA_ROWS 128   // rows per CTA: the staging of the eigenvectors is amortised over 128 x N outputs
+#endif
 __global__ void __launch_bounds__(256) reconstruct_kernel(const double* __restrict__ V, const double* __restrict__ lamall,
                                                           const int* __restrict__ nfall,
                                                           const double* __restrict__ sigmaall, int N,

@@ -446,7 +446,9 @@ int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double
 // reflectors of one sweep act on disjoint row windows, so a sweep is one parallel step over (reflector, vector) pairs;
 // sweeps run last to first.  The vectors sit in shared memory as Y[row][vector].
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef Q2B_NT
 #define Q2B_NT 256
+#endif
 #define Q2B_V 16   // = EV3_VMAX
 
 __global__ void __launch_bounds__(Q2B_NT) q2back_kernel(const double* __restrict__ Q2all, const int* __restrict__ nfall,
