@@ -244,7 +244,9 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
 // section per step).  Same guarded decisions as hrp_tree_kernel<1>; the first ambiguous one flags the simulation and
 // ends the warp.  edges[s][0][k], [1][k], [2][k] = x, y and the tree node that realises best[y] of step k.
 // ---------------------------------------------------------------------------------------------------------------
-#define PR_WARPS 4
+#ifndef PR_WARPS
+#define PR_WARPS 2   // measured (us per simulation at N = 500): 2 -> 0.58, 4 -> 0.66, 8 -> 0.85
+#endif
 template <int MAXM>
 __global__ void __launch_bounds__(PR_WARPS * 32) hrp_prim_kernel(const double* __restrict__ E2all,
                                                                  const double* __restrict__ rnall, int N, int S,

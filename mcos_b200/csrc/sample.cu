@@ -42,6 +42,9 @@ __device__ __forceinline__ void normal_pair(uint64_t sim, uint32_t t, uint32_t p
     z1 = rad * sn;
 }
 
+#ifndef PHILOX_CTAS_PER_SM
+#define PHILOX_CTAS_PER_SM 16
+#endif
 // One warp per row (s, t) of Z[S][T][N], lanes over the pairs of that row, grid-stride over rows: the 64-bit divisions that
 // turn a flat pair index into (s, t, p) -- about a third of the instructions when done per pair -- happen once per row.
 __global__ void __launch_bounds__(256) philox_normal_kernel(double* __restrict__ Z, uint64_t sim_id0, int S, int T,
@@ -241,7 +244,7 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     const size_t M = (size_t)S * T;
     double* dZ = nullptr;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_Z, M * N, &dZ));
-    int grid = (int)std::min<size_t>((M + 7) / 8, (size_t)ctx->num_sms * 16);   // 8 warps = 8 rows per CTA and pass
+    int grid = (int)std::min<size_t>((M + 7) / 8, (size_t)ctx->num_sms * PHILOX_CTAS_PER_SM);   // 8 warps = 8 rows per CTA and pass
     philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
     MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
     size_t row_tiles = (M + DM_BM - 1) / DM_BM;
