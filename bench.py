@@ -233,6 +233,10 @@ def run_native(args):
     plan = mb.build_plan(sim, optimizers, estimator, transformers)
     eng = get_engine(N_ASSETS, N_OBS, local, args.seed)
     eng.ensure_truth(mu, cov)          # inputs resident in HBM before the timed region
+    # one explicit stream for everything: the kernels are launched on it and the CUDA events that time them are
+    # recorded on it (torch.cuda.Event sees only torch's current stream)
+    bench_stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(bench_stream)
     eng.use_torch_stream()
 
     def step(i, out_torch=True):

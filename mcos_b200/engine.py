@@ -65,6 +65,9 @@ class Engine:
 
     def _out(self, like_torch, shape, dtype=np.float64):
         if like_torch:
+            # device tensors in, device tensors out: nothing synchronises with the host, so the kernels must run on the
+            # stream the caller's torch work is on
+            self.use_torch_stream()
             t = torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32,
                             device=f"cuda:{self.device}")
             return t, ctypes.c_void_p(t.data_ptr())
@@ -72,8 +75,11 @@ class Engine:
         return a, a.ctypes.data_as(ctypes.c_void_p)
 
     def use_torch_stream(self):
-        """Binds the context to torch's current CUDA stream on this device."""
-        self._check(self.lib.mcosb_set_stream(self.h, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        """Binds the context to torch's current CUDA stream on this device.  torch's default stream has handle 0, which
+        mcosb_set_stream reads as "the context's own stream": it is passed as cudaStreamLegacy (0x1) instead, so that the
+        library's kernels are ordered with the torch work around them."""
+        handle = torch.cuda.current_stream(self.device).cuda_stream or 0x1
+        self._check(self.lib.mcosb_set_stream(self.h, ctypes.c_void_p(handle)))
 
     def synchronize(self):
         self._check(self.lib.mcosb_synchronize(self.h))

@@ -120,3 +120,25 @@ def test_hrp_ties_take_the_fallback():
     w, info = eng.hrp(np.stack([cov, cov]))
     assert eng.hrp_fallback_count() == 2
     _check(cov, w, info, 1)
+
+
+def test_device_tensors_are_ordered_with_torch_work():
+    """Device tensors in and out: nothing synchronises with the host, so the kernels must run on the stream the caller's
+    torch work is on.  (torch's default stream has handle 0, which mcosb_set_stream reads as "own stream"; the engine
+    passes cudaStreamLegacy instead.)  Exact distances for 256 matrices take milliseconds: a copy that does not wait
+    for them returns uninitialised memory."""
+    import torch
+    n, t, nsim = 300, 600, 256
+    mu, cov = block_diagonal_truth(n)
+    eng = Engine(n, t, seed=9)
+    eng.set_truth(mu, cov)
+    x = eng.sample(nsim)
+    _, covs, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
+    eng.set_hrp_mode(1)
+    w_ref, info_ref = eng.hrp(covs)                                   # host buffers: staged and synchronised
+    w, info = eng.hrp(torch.from_numpy(covs).cuda())                  # device tensors on torch's current (default) stream
+    order, link, w = info["order"].cpu().numpy(), info["linkage"].cpu().numpy(), w.cpu().numpy()
+    eng.set_hrp_mode(0)
+    assert np.array_equal(order, info_ref["order"])
+    assert np.array_equal(link, info_ref["linkage"])
+    assert np.array_equal(w, w_ref)
