@@ -64,7 +64,9 @@ int mcosb_create(mcosb_ctx** out, int device, int n_assets, int n_obs, uint64_t 
 int mcosb_destroy(mcosb_ctx* ctx);
 const char* mcosb_last_error(const mcosb_ctx* ctx);
 
-/* Binds the context to a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+/* Binds the context to a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own
+ * (non-blocking) stream.  The CUDA default stream has handle 0 = NULL: to run on it pass cudaStreamLegacy ((void*)0x1)
+ * or cudaStreamPerThread ((void*)0x2).  Calls with device pointers are asynchronous on the bound stream. */
 int mcosb_set_stream(mcosb_ctx* ctx, void* cuda_stream);
 /* Blocks until all work queued on the context's stream has finished. */
 int mcosb_synchronize(mcosb_ctx* ctx);
