@@ -1,10 +1,13 @@
 // FP64 tensor-core (DMMA) tile machinery shared by the moments SYRK and the sampling TRMM.
 //
 // tcgen05 has no f64 kind, so the FP64 tensor path on sm_100a is the warp-level mma.sync m8n8k4 (SASS DMMA.8x8x4;
-// measured 37.0 TFLOP/s on B200, profiles/fp64_peaks_r01.json).  A CTA of 256 threads (8 warps as 2 x 4) owns a
-// 128 x 128 FP64 accumulator tile; each warp owns 64 x 32 of it as 8 x 4 m8n8 blocks = 64 doubles per thread.
-// Operand tiles move global -> shared with cp.async (LDGSTS, 8-byte, zero-fill for the ragged edges) through a
-// DM_STAGES-deep ring, one __syncthreads per k-slab.
+// measured 37.0 TFLOP/s on B200, profiles/fp64_peaks_r01.json).  A warp owns 64 x 32 of the FP64 accumulator tile as
+// 8 x 4 m8n8 blocks = 64 doubles per thread.  The kernels built on this (trmm2, syrk, hrp_gram) run CTAs of 4 warps
+// (2 x 2: a 128 x 64 tile, or one of the two warp sets of a diagonal 128 x 128 tile), two CTAs per SM, so that the
+// prologue / epilogue of one CTA overlaps the main loop of the other; the original 8-warp / 128 x 128 TRMM is kept for
+// A/B runs.  Operand tiles move global -> shared with cp.async (LDGSTS, 16-byte when the alignment allows, zero-fill
+// for the ragged edges) through a DM_STAGES-deep ring, one __syncthreads per k-slab; the copies of stage kt + 2 are
+// issued after the first k-step of slab kt so that they interleave with DMMAs already queued.
 #pragma once
 #include <type_traits>
 
