@@ -19,7 +19,10 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
                          const double* Q2);
 
 // ---------------------------------------------------------------------------------------------------------------
-// D1: correlation matrix.  grid = (ceil(N/32), S), 256 threads, 4 rows per warp; the CTA takes the N square roots of
+#ifndef CORR_ROWS
+#define CORR_ROWS 32   // rows per CTA (a multiple of 8)
+#endif
+// D1: correlation matrix.  grid = (ceil(N / CORR_ROWS), S), 256 threads, CORR_ROWS / 8 rows per warp; the CTA takes the N square roots of
 // the diagonal once (strided reads) into shared memory instead of once per row.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) corr_kernel(const double* __restrict__ cov, int N, double* __restrict__ A,
@@ -38,8 +41,8 @@ __global__ void __launch_bounds__(256) corr_kernel(const double* __restrict__ co
         sg[j] = sqrt(v);
     }
     __syncthreads();
-    for (int r = 0; r < 4; ++r) {
-        const int row = blockIdx.x * 32 + wid * 4 + r;
+    for (int r = 0; r < CORR_ROWS / 8; ++r) {
+        const int row = blockIdx.x * CORR_ROWS + wid * (CORR_ROWS / 8) + r;
         if (row >= N) return;
         const double si = sg[row];
         if (lane == 0) sigma[(size_t)s * N + row] = si;
@@ -930,7 +933,7 @@ int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, 
                           double* tau, double* lam, const double** q2, const double* lwcoef) {
     const int N = ctx->N;
     const size_t n = (size_t)N;
-    corr_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, A, sigma, lwcoef);
+    corr_kernel<<<dim3((N + CORR_ROWS - 1) / CORR_ROWS, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, A, sigma, lwcoef);
     MCOSB_LAUNCHED(ctx, MK_CORR);
     MCOSB_TRY(mcosb_dev_tridiagonalize(ctx, S, A, d, e, tau, q2));
     size_t smem_ev = 2 * n * sizeof(double) + n * sizeof(int);

@@ -19,7 +19,10 @@
 #include "dmma.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
-// grid = (ceil(N/32), S), 4 rows per warp; the square roots of the diagonal are taken once per CTA (shared memory).
+#ifndef HD_ROWS
+#define HD_ROWS 32   // rows per CTA (a multiple of 8)
+#endif
+// grid = (ceil(N / HD_ROWS), S), HD_ROWS / 8 rows per warp; the square roots of the diagonal are taken once per CTA.
 // (1 - r) / 2 is an exact halving, so the multiplication by 0.5 rounds like numpy's division.
 __global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D,
                                                        double* __restrict__ rn) {
@@ -30,8 +33,8 @@ __global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict_
     double* d = D + (size_t)s * N * N;
     for (int j = threadIdx.x; j < N; j += 256) sg[j] = sqrt(c[(size_t)j * N + j]);
     __syncthreads();
-    for (int q = 0; q < 4; ++q) {
-        const int row = blockIdx.x * 32 + wid * 4 + q;
+    for (int q = 0; q < HD_ROWS / 8; ++q) {
+        const int row = blockIdx.x * HD_ROWS + wid * (HD_ROWS / 8) + q;
         if (row >= N) return;
         const double si = sg[row];
         double nrm = 0.0;
@@ -721,7 +724,7 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_RN, (size_t)S * n, &rn));
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_FLAG, (size_t)S, &slow));
     }
-    hrp_dist_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, D, rn);
+    hrp_dist_kernel<<<dim3((N + HD_ROWS - 1) / HD_ROWS, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, D, rn);
     MCOSB_LAUNCHED(ctx, MK_HRP_DIST);
     int* order = dorder;
     if (!order) MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_ORDER, (size_t)S * n, &order));
