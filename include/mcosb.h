@@ -35,13 +35,15 @@ enum {
     MCOSB_ERR_STATE = -3,    /* e.g. truth not set */
     MCOSB_ERR_NOT_PD = -4,   /* true covariance is not positive definite (Cholesky failed) */
     MCOSB_ERR_IDEAL = -5     /* mcosb_run: an optimizer failed on the TRUE (mu, cov) (mcos.py:30 would raise); the
-                                MCOSB_ST_* bits are the last integer of mcosb_last_error */
+                                MCOSB_ST_* bits are the last integer of mcosb_last_error.  MCOSB_ST_NO_EXCESS alone is
+                                not a failure */
 };
 
 /* per-simulation status bits */
 enum {
     MCOSB_ST_NOT_PD = 1,          /* a Cholesky pivot was <= 0 (Markowitz free-set system, NCO cluster solve) */
-    MCOSB_ST_NO_EXCESS = 2,       /* Markowitz: no asset with mu_i > rf; weights are NaN */
+    MCOSB_ST_NO_EXCESS = 2,       /* Markowitz: no asset with mu_i > rf; the allocation is the single asset with the best
+                                     (least negative) stand-alone Sharpe ratio -- informational, not a failure */
     MCOSB_ST_QP_CAP = 4,          /* Markowitz: active-set iteration cap reached */
     MCOSB_ST_MPFIT_FAIL = 8,      /* DeNoiser: line search failed -> var = 1 (covariance_transformer.py:127-130) */
     MCOSB_ST_EIGVEC = 16,         /* DeNoiser: an eigenvector residual check failed */
@@ -53,8 +55,11 @@ enum {
 enum { MCOSB_MOMENTS_MUCOV = 0, MCOSB_MOMENTS_LEDOIT_WOLF = 1, MCOSB_MOMENTS_JACKKNIFE = 2 };
 /* error estimators: error_estimator.py:21-25 / 28-32 / 35-41 */
 enum { MCOSB_ERR_EXPECTED_OUTCOME = 0, MCOSB_ERR_VARIANCE = 1, MCOSB_ERR_SHARPE = 2 };
-/* optimizers for mcosb_run: optimizer.py:41-53 / 198-287 / 56-195 / 290-359 (equal risk budget) */
+/* optimizers for mcosb_run: optimizer.py:41-53 / 198-287 / 56-195 / 290-359 */
 enum { MCOSB_OPT_MARKOWITZ = 0, MCOSB_OPT_HRP = 1, MCOSB_OPT_NCO = 2, MCOSB_OPT_RISK_PARITY = 3 };
+/* covariance transformers for mcosb_run: covariance_transformer.py:55-208 / 211-250 */
+enum { MCOSB_TR_DENOISE = 0, MCOSB_TR_DETONE = 1 };
+#define MCOSB_MAX_TRANSFORMERS 4
 
 int mcosb_version(void);
 
@@ -143,6 +148,11 @@ int mcosb_risk_parity(mcosb_ctx* ctx, int S, const double* cov, const double* bu
  * w[S][N]; w_star is [S][N] if w_star_batched else [N] (the loop-invariant ideal allocation, mcos.py:30). */
 int mcosb_errors(mcosb_ctx* ctx, int S, const double* w, const double* w_star, int w_star_batched, int kind,
                  double* err);
+/* The same for several estimators in one pass over the weights: err[S][n_kinds], kinds[k] = MCOSB_ERR_*, 1 <= n_kinds
+ * <= 3.  Column k is bit-identical to mcosb_errors(..., kinds[k], ...) (the three estimators share delta.mu and
+ * delta' Cov delta, error_estimator.py:44-49). */
+int mcosb_errors_multi(mcosb_ctx* ctx, int S, const double* w, const double* w_star, int w_star_batched, int n_kinds,
+                       const int* kinds, double* err);
 
 /* The whole loop body of mcos.py:22-33 for simulations sim_id0 .. sim_id0+S-1, stages chained on the device. */
 typedef struct mcosb_plan {
@@ -157,10 +167,20 @@ typedef struct mcosb_plan {
     int nco_trials;          /* NCO: num_clustering_trials */
     int wave;                /* simulations per wave (0 = choose from free memory) */
     int detone_n_remove;     /* > 0: apply DetoneCovarianceTransformer(n_remove) after the DeNoiser */
+    /* ---- version >= 200 (zero-initialise for the behaviour above) ------------------------------------------------- */
+    int n_error_kinds;       /* 0: one estimator, `error_kind`.  1..3: all of error_kinds[] from ONE pass over the
+                                simulations (the estimators are an O(N^2) epilogue on the same weights) */
+    int error_kinds[3];      /* MCOSB_ERR_* */
+    int n_transformers;      /* 0: `denoise` / `detone_n_remove` above.  1..MCOSB_MAX_TRANSFORMERS: the list below,
+                                applied in order (mcos.py:25-26 applies any list in order) */
+    int transformer_kind[MCOSB_MAX_TRANSFORMERS];    /* MCOSB_TR_* */
+    double transformer_arg[MCOSB_MAX_TRANSFORMERS];  /* DeNoiser: bandwidth; Detone: n_remove */
+    const double* risk_budget;  /* RiskParityOptimizer(target_risk)[N] (optimizer.py:295-309), host or device pointer;
+                                   NULL = equal budget 1/N */
 } mcosb_plan;
 
-/* err[S][n_optimizers]; status[S] nullable.  The ideal allocations (optimizer.allocate(true mu, true cov)) are
- * computed once per call instead of once per simulation. */
+/* err[S][n_optimizers] (err[S][n_optimizers][n_error_kinds] when plan->n_error_kinds > 0); status[S] nullable.  The
+ * ideal allocations (optimizer.allocate(true mu, true cov)) are computed once per call instead of once per simulation. */
 int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id0, int S, double* err, int* status);
 
 /* Per-stage device time (ms) of the last mcosb_run, accumulated over waves, measured with CUDA events on the

@@ -11,7 +11,7 @@ from .covariance_transformer import (AbstractCovarianceTransformer, DeNoiserCova
 from .error_estimator import (AbstractErrorEstimator, ExpectedOutcomeErrorEstimator, SharpeRatioErrorEstimator,
                               VarianceErrorEstimator)
 from .mcos import (build_plan, shard_range, simulate_errors, simulate_optimizations,
-                   simulate_optimizations_from_price_history, summarize_errors)
+                   simulate_optimizations_from_price_history, status_counts, summarize_errors)
 from .observation_simulator import (AbstractObservationSimulator, MuCovJackknifeObservationSimulator,
                                     MuCovLedoitWolfObservationSimulator, MuCovObservationSimulator)
 from .optimizer import AbstractOptimizer, HRPOptimizer, MarkowitzOptimizer, NCOOptimizer, RiskParityOptimizer

@@ -15,9 +15,13 @@ STAGE_NAMES = ("sample", "moments", "denoise", "markowitz", "hrp", "nco", "error
 MOMENTS_MUCOV, MOMENTS_LEDOIT_WOLF, MOMENTS_JACKKNIFE = 0, 1, 2
 ERR_EXPECTED_OUTCOME, ERR_VARIANCE, ERR_SHARPE = 0, 1, 2
 OPT_MARKOWITZ, OPT_HRP, OPT_NCO, OPT_RISK_PARITY = 0, 1, 2, 3
+TR_DENOISE, TR_DETONE = 0, 1
+MAX_TRANSFORMERS = 4
 
 ERR_IDEAL = -5
 ST_NOT_PD, ST_NO_EXCESS, ST_QP_CAP, ST_MPFIT_FAIL, ST_EIGVEC, ST_HRP_SUM, ST_NONFINITE = 1, 2, 4, 8, 16, 32, 64
+ST_NAMES = {ST_NOT_PD: "NOT_PD", ST_NO_EXCESS: "NO_EXCESS", ST_QP_CAP: "QP_CAP", ST_MPFIT_FAIL: "MPFIT_FAIL",
+            ST_EIGVEC: "EIGVEC", ST_HRP_SUM: "HRP_SUM", ST_NONFINITE: "NONFINITE"}
 
 
 class MCOSBError(RuntimeError):
@@ -27,7 +31,10 @@ class MCOSBError(RuntimeError):
 class Plan(ctypes.Structure):
     _fields_ = [("moments_kind", c_int), ("denoise", c_int), ("bandwidth", c_double), ("n_optimizers", c_int),
                 ("optimizers", c_int * 4), ("error_kind", c_int), ("risk_free_rate", c_double),
-                ("nco_max_clusters", c_int), ("nco_trials", c_int), ("wave", c_int), ("detone_n_remove", c_int)]
+                ("nco_max_clusters", c_int), ("nco_trials", c_int), ("wave", c_int), ("detone_n_remove", c_int),
+                ("n_error_kinds", c_int), ("error_kinds", c_int * 3), ("n_transformers", c_int),
+                ("transformer_kind", c_int * MAX_TRANSFORMERS), ("transformer_arg", c_double * MAX_TRANSFORMERS),
+                ("risk_budget", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/mcosb.h declares
@@ -52,6 +59,7 @@ SIGNATURES = {
     "mcosb_nco": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_risk_parity": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_errors": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mcosb_errors_multi": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, POINTER(c_int), c_void_p]),
     "mcosb_run": (c_int, [c_void_p, POINTER(Plan), c_uint64, c_int, c_void_p, c_void_p]),
     "mcosb_last_stage_ms": (c_int, [c_void_p, POINTER(c_double)]),
     "mcosb_launch_count": (c_longlong, [c_void_p]),

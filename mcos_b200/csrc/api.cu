@@ -1,7 +1,7 @@
 // Context lifetime, truth upload (+ one-off Cholesky), and the error-estimator kernel (K5).
 #include "common.cuh"
 
-extern "C" int mcosb_version(void) { return 100; }
+extern "C" int mcosb_version(void) { return 200; }
 
 extern "C" int mcosb_create(mcosb_ctx** out, int device, int n_assets, int n_obs, uint64_t seed) {
     if (!out || n_assets < 1 || n_obs < 1) return MCOSB_ERR_ARG;
@@ -145,8 +145,16 @@ extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* c
 __global__ void __launch_bounds__(ERR_THREADS) errors_kernel(const double* __restrict__ w,
                                                              const double* __restrict__ wstar, int batched,
                                                              const double* __restrict__ mu,
-                                                             const double* __restrict__ cov, int n, int S, int kind,
-                                                             double* __restrict__ err, int ld) {
+                                                             const double* __restrict__ cov, int n, int S, int nk,
+                                                             int k0, int k1, int k2, double* __restrict__ err, int ld) {
+    // the kinds wanted, in output order: err[s * ld + k] = estimator kinds[k]; Var / EO are formed only if some kind
+    // needs them, with the same instructions whatever else is asked for (bit-equal to the single-kind call)
+    const int kinds[3] = {k0, k1, k2};
+    bool need_var = false, need_eo = false;
+    for (int k = 0; k < nk; ++k) {
+        need_var |= kinds[k] != MCOSB_ERR_EXPECTED_OUTCOME;
+        need_eo |= kinds[k] != MCOSB_ERR_VARIANCE;
+    }
     extern __shared__ double sm[];
     double* delta = sm;                  // [ERR_SB][n]
     double* red = sm + (size_t)ERR_SB * n;  // [ERR_THREADS/32][ERR_SB][2]
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(ERR_THREADS) errors_kernel(const double* __res
     double var_acc[ERR_SB], eo_acc[ERR_SB];
 #pragma unroll
     for (int s = 0; s < ERR_SB; ++s) var_acc[s] = eo_acc[s] = 0.0;
-    if (kind != MCOSB_ERR_EXPECTED_OUTCOME) {
+    if (need_var) {
         for (int i = wid; i < n; i += nw) {
             double t[ERR_SB];
 #pragma unroll
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(ERR_THREADS) errors_kernel(const double* __res
             }
         }
     }
-    if (kind != MCOSB_ERR_VARIANCE) {
+    if (need_eo) {
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             double m = mu[j];
 #pragma unroll
@@ -208,25 +216,32 @@ __global__ void __launch_bounds__(ERR_THREADS) errors_kernel(const double* __res
             var += red[(k * ERR_SB + s) * 2 + 0];
             eo += red[(k * ERR_SB + s) * 2 + 1];
         }
-        double out;
-        if (kind == MCOSB_ERR_EXPECTED_OUTCOME) out = eo;
-        else if (kind == MCOSB_ERR_VARIANCE) out = var;
-        else out = eo / sqrt(var);
-        err[(size_t)(s0 + s) * ld] = out;
+        for (int k = 0; k < nk; ++k) {
+            double out;
+            if (kinds[k] == MCOSB_ERR_EXPECTED_OUTCOME) out = eo;
+            else if (kinds[k] == MCOSB_ERR_VARIANCE) out = var;
+            else out = eo / sqrt(var);
+            err[(size_t)(s0 + s) * ld + k] = out;
+        }
     }
 }
 
-int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int kind,
-                     double* derr, int ld) {
+int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int nk,
+                     const int* kinds, double* derr, int ld) {
     if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
-    if (kind < 0 || kind > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown error estimator kind");
+    if (nk < 1 || nk > 3 || !kinds) return mcosb_fail(ctx, MCOSB_ERR_ARG, "between 1 and 3 error estimator kinds");
+    int kk[3] = {0, 0, 0};
+    for (int k = 0; k < nk; ++k) {
+        if (kinds[k] < 0 || kinds[k] > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown error estimator kind");
+        kk[k] = kinds[k];
+    }
     if (S == 0) return MCOSB_OK;
     size_t smem = ((size_t)ERR_SB * ctx->N + (ERR_THREADS / 32) * ERR_SB * 2) * sizeof(double);
     if (smem > 48 * 1024)
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(errors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (S + ERR_SB - 1) / ERR_SB;
     errors_kernel<<<grid, ERR_THREADS, smem, ctx->stream>>>(dw, dwstar, batched, ctx->d_mu, ctx->d_cov, ctx->N, S,
-                                                           kind, derr, ld);
+                                                           nk, kk[0], kk[1], kk[2], derr, ld);
     MCOSB_LAUNCHED(ctx, MK_ERRORS);
     return MCOSB_OK;
 }
@@ -242,7 +257,23 @@ extern "C" int mcosb_errors(mcosb_ctx* ctx, int S, const double* w, const double
     MCOSB_TRY(st.in(w, (size_t)S * n, SL_STAGE_IN0, &dw));
     MCOSB_TRY(st.in(w_star, w_star_batched ? (size_t)S * n : n, SL_STAGE_IN1, &dws));
     MCOSB_TRY(st.out(err, (size_t)S, SL_STAGE_OUT0, &derr));
-    MCOSB_TRY(mcosb_dev_errors(ctx, S, dw, dws, w_star_batched, kind, derr, 1));
+    MCOSB_TRY(mcosb_dev_errors(ctx, S, dw, dws, w_star_batched, 1, &kind, derr, 1));
+    return st.finish();
+}
+
+extern "C" int mcosb_errors_multi(mcosb_ctx* ctx, int S, const double* w, const double* w_star, int w_star_batched,
+                                  int n_kinds, const int* kinds, double* err) {
+    MCOSB_CHECK_CTX(ctx);
+    if (S < 0 || !w || !w_star || !err || !kinds || n_kinds < 1 || n_kinds > 3)
+        return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_errors_multi");
+    size_t n = (size_t)ctx->N;
+    Staging st(ctx);
+    const double *dw, *dws;
+    double* derr;
+    MCOSB_TRY(st.in(w, (size_t)S * n, SL_STAGE_IN0, &dw));
+    MCOSB_TRY(st.in(w_star, w_star_batched ? (size_t)S * n : n, SL_STAGE_IN1, &dws));
+    MCOSB_TRY(st.out(err, (size_t)S * n_kinds, SL_STAGE_OUT0, &derr));
+    MCOSB_TRY(mcosb_dev_errors(ctx, S, dw, dws, w_star_batched, n_kinds, kinds, derr, n_kinds));
     return st.finish();
 }
 

@@ -19,7 +19,7 @@ enum ScratchSlot {
     SL_MK_L, SL_MK_W, SL_MK_ITERS,
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
     SL_NCO_W, SL_NCO_LABELS, SL_NCO_WORK, SL_NCO_E,
-    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2,
+    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2, SL_NCO_CENTERS,
     SL_COUNT
 };
 
@@ -321,6 +321,6 @@ int mcosb_dev_markowitz(mcosb_ctx* ctx, int S, const double* dmu, const double* 
 int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* dorder, double* dlink, int* dstatus);
 int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, int max_k, int trials,
                   const int* dlabels_in, double* dw, int* dlabels_out, int* dstatus);
-// derr[s * ld] receives the error of simulation s (ld = 1 for a plain vector, n_optimizers for a column of the table)
-int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int kind,
-                     double* derr, int ld);
+// derr[s * ld + k] receives estimator kinds[k] (k < nk <= 3, host array) of simulation s
+int mcosb_dev_errors(mcosb_ctx* ctx, int S, const double* dw, const double* dwstar, int batched, int nk,
+                     const int* kinds, double* derr, int ld);

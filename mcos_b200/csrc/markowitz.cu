@@ -180,11 +180,34 @@ __global__ void __launch_bounds__(MK_THREADS) markowitz_kernel(const double* __r
     double bv;
     int start;
     block_argmin(best, besti, s, bv, start);
-    if (__syncthreads_or(st) || start >= N || !(bv < 0.0)) {
+    if (__syncthreads_or(st)) {
         for (int i = tid; i < N; i += MK_THREADS) w[i] = NAN;
         if (tid == 0) {
             if (iters_out) iters_out[sim] = 0;
-            if (status) status[sim] |= (st ? MCOSB_ST_NONFINITE : MCOSB_ST_NO_EXCESS);
+            if (status) status[sim] |= MCOSB_ST_NONFINITE;
+        }
+        return;
+    }
+    if (start >= N || !(bv < 0.0)) {
+        // No asset beats the risk-free rate.  The QP reformulation does not apply; the stated problem
+        // max (w.mu - rf) / sqrt(w'Cw) on the simplex then has a non-positive numerator everywhere, its objective is
+        // quasi-convex and the maximum sits at a vertex: the single asset with the largest (least negative) stand-alone
+        // Sharpe ratio.  (The reference hands this case to SLSQP, which also stops at a vertex -- a local one.)  The
+        // simulation is flagged MCOSB_ST_NO_EXCESS but keeps a defined allocation.
+        best = INFINITY;
+        besti = N;
+        for (int i = tid; i < N; i += MK_THREADS) {
+            const double d = C[(size_t)i * N + i];
+            if (d > 0.0) {
+                const double score = -(s.c[i] / sqrt(d));
+                if (score < best) { best = score; besti = i; }
+            }
+        }
+        block_argmin(best, besti, s, bv, start);
+        for (int i = tid; i < N; i += MK_THREADS) w[i] = (start < N) ? (i == start ? 1.0 : 0.0) : NAN;
+        if (tid == 0) {
+            if (iters_out) iters_out[sim] = 0;
+            if (status) status[sim] |= MCOSB_ST_NO_EXCESS | (start < N ? 0 : MCOSB_ST_NOT_PD);
         }
         return;
     }

@@ -194,12 +194,15 @@ __global__ void __launch_bounds__(NC_THREADS_MAX) nco_cluster_kernel(const doubl
                                                                  const double* __restrict__ Eall, int N, int max_k,
                                                                  const double* __restrict__ uni,  // [max_k+1][ustride]
                                                                  int ustride, int* __restrict__ labels_out,
-                                                                 double* __restrict__ quality_out) {
+                                                                 double* __restrict__ quality_out,
+                                                                 double* __restrict__ gwork) {
     extern __shared__ double sm[];
     NcSm s;
-    s.centers = sm;
+    // centres / new centres / silhouette sums [2][max_k][N]: in shared memory when they fit, otherwise in per-simulation
+    // global scratch (the reference's default max_num_clusters = N / 2 needs 8 N^2 bytes: 2 MB at N = 500)
+    s.centers = gwork ? gwork + (size_t)blockIdx.x * 2 * max_k * N : sm;
     s.cnew = s.centers + (size_t)max_k * N;
-    s.xnorm = s.cnew + (size_t)max_k * N;
+    s.xnorm = gwork ? sm : s.cnew + (size_t)max_k * N;
     s.closest = s.xnorm + N;
     s.cand = s.cnew;          // k-means++ candidate distances [ncg][N]: cnew is free until Lloyd starts
     s.bestd = s.xnorm;
@@ -622,13 +625,19 @@ int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, 
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_NCO_E, tab.size(), &duni));
         MCOSB_CUDA(ctx, cudaMemcpyAsync(duni, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tab` is a pageable stack-owned buffer
-        size_t smem = (2 * (size_t)max_k * n + 3 * n + 2 * (size_t)max_k + 64) * sizeof(double) +
-                      (4 * n + 2 * (size_t)max_k + 33 + NC_CG) * sizeof(int);
-        if (smem > (size_t)ctx->smem_optin)
-            return mcosb_fail(ctx, MCOSB_ERR_ARG, "max_num_clusters x n_assets too large for nco_cluster_kernel's shared memory");
+        const size_t small = (3 * n + 2 * (size_t)max_k + 64) * sizeof(double) +
+                             (4 * n + 2 * (size_t)max_k + 33 + NC_CG + 1) * sizeof(int);
+        size_t smem = small + 2 * (size_t)max_k * n * sizeof(double);
+        double* gwork = nullptr;
+        if (smem > (size_t)ctx->smem_optin) {
+            smem = small;
+            if (smem > (size_t)ctx->smem_optin)
+                return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_assets too large for nco_cluster_kernel's shared memory");
+            MCOSB_TRY(mcosb_scratch_t(ctx, SL_NCO_CENTERS, (size_t)S * 2 * max_k * n, &gwork));
+        }
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(nco_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         nco_cluster_kernel<<<S, N >= 512 ? NC_THREADS_MAX : (N <= 128 ? 128 : NC_THREADS), smem, ctx->stream>>>(D, E, N, max_k, duni, ustride, labels,
-                                                                                         nullptr);
+                                                                                         nullptr, gwork);
         MCOSB_LAUNCHED(ctx, MK_NCO_CLUSTER);
     }
     double* work;

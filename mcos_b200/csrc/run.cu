@@ -13,8 +13,42 @@
 #define RUN_CHUNK_BYTES ((size_t)4 << 30)
 #endif
 
-int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W, const double* d_ideal, double* derr,
-                   int* dstatus, std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>& marks) {
+// The plan with its defaults resolved: transformer list (legacy fields or the explicit list), estimator kinds, device
+// pointer of the risk budget.
+struct RunPlan {
+    int ntr = 0;
+    int tr_kind[MCOSB_MAX_TRANSFORMERS] = {};
+    double tr_arg[MCOSB_MAX_TRANSFORMERS] = {};
+    int nk = 1;
+    int kinds[3] = {0, 0, 0};
+    const double* d_budget = nullptr;
+};
+
+static int resolve_plan(mcosb_ctx* ctx, const mcosb_plan* plan, RunPlan& rp) {
+    if (plan->n_transformers < 0 || plan->n_transformers > MCOSB_MAX_TRANSFORMERS)
+        return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_transformers must be 0..4");
+    if (plan->n_transformers > 0) {
+        for (int i = 0; i < plan->n_transformers; ++i) {
+            const int k = plan->transformer_kind[i];
+            if (k != MCOSB_TR_DENOISE && k != MCOSB_TR_DETONE) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown transformer kind");
+            if (k == MCOSB_TR_DETONE && (int)plan->transformer_arg[i] == 0) continue;   // the identity
+            rp.tr_kind[rp.ntr] = k;
+            rp.tr_arg[rp.ntr++] = plan->transformer_arg[i];
+        }
+    } else {
+        if (plan->denoise) { rp.tr_kind[rp.ntr] = MCOSB_TR_DENOISE; rp.tr_arg[rp.ntr++] = plan->bandwidth; }
+        if (plan->detone_n_remove > 0) { rp.tr_kind[rp.ntr] = MCOSB_TR_DETONE; rp.tr_arg[rp.ntr++] = plan->detone_n_remove; }
+    }
+    if (plan->n_error_kinds < 0 || plan->n_error_kinds > 3) return mcosb_fail(ctx, MCOSB_ERR_ARG, "n_error_kinds must be 0..3");
+    if (plan->n_error_kinds == 0) { rp.nk = 1; rp.kinds[0] = plan->error_kind; }
+    else { rp.nk = plan->n_error_kinds; for (int k = 0; k < rp.nk; ++k) rp.kinds[k] = plan->error_kinds[k]; }
+    for (int k = 0; k < rp.nk; ++k)
+        if (rp.kinds[k] < 0 || rp.kinds[k] > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown error estimator kind");
+    return MCOSB_OK;
+}
+
+int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, const RunPlan& rp, uint64_t sim0, int W, const double* d_ideal,
+                   double* derr, int* dstatus, std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>>& marks) {
     const size_t N = ctx->N, T = ctx->T;
     double *dmu, *dcov;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_MUHAT, (size_t)W * N, &dmu));
@@ -36,7 +70,7 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
     // Ledoit-Wolf followed by the de-noiser: the shrink (one read-modify-write of every covariance matrix) is folded
     // into the de-noiser's covariance -> correlation pass, which is the only consumer of the shrunk matrix
     double* lwcoef = nullptr;
-    if (plan->moments_kind == MCOSB_MOMENTS_LEDOIT_WOLF && plan->denoise)
+    if (plan->moments_kind == MCOSB_MOMENTS_LEDOIT_WOLF && rp.ntr > 0 && rp.tr_kind[0] == MCOSB_TR_DENOISE)
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWCOEF, 2 * (size_t)W, &lwcoef));
     for (int c0 = 0; c0 < W; c0 += CH) {
         const int nc = std::min(CH, W - c0);
@@ -48,14 +82,13 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
                                     nullptr, lwcoef ? lwcoef + 2 * (size_t)c0 : nullptr));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, false));
     }
-    if (plan->denoise) {
+    for (int i = 0; i < rp.ntr; ++i) {   // any list, in order (mcos.py:25-26)
         MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, true));
-        MCOSB_TRY(mcosb_dev_denoise(ctx, W, dcov, ctx->T, plan->bandwidth, nullptr, nullptr, nullptr, dstatus, lwcoef));
-        MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, false));
-    }
-    if (plan->detone_n_remove > 0) {
-        MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, true));
-        MCOSB_TRY(mcosb_dev_detone(ctx, W, dcov, plan->detone_n_remove, dstatus));
+        if (rp.tr_kind[i] == MCOSB_TR_DENOISE)
+            MCOSB_TRY(mcosb_dev_denoise(ctx, W, dcov, ctx->T, rp.tr_arg[i], nullptr, nullptr, nullptr, dstatus,
+                                        i == 0 ? lwcoef : nullptr));
+        else
+            MCOSB_TRY(mcosb_dev_detone(ctx, W, dcov, (int)rp.tr_arg[i], dstatus));
         MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, false));
     }
     double* dw;
@@ -74,7 +107,7 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
         } else if (kind == MCOSB_OPT_RISK_PARITY) {
             stage = MCOSB_STAGE_NCO;   // reported with the "other optimizers" stage timer
             MCOSB_TRY(mark(stage, true));
-            MCOSB_TRY(mcosb_dev_risk_parity(ctx, W, dcov, nullptr, dw, nullptr, dstatus));
+            MCOSB_TRY(mcosb_dev_risk_parity(ctx, W, dcov, rp.d_budget, dw, nullptr, dstatus));
         } else {
             stage = MCOSB_STAGE_NCO;
             MCOSB_TRY(mark(stage, true));
@@ -83,8 +116,8 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim0, int W,
         }
         MCOSB_TRY(mark(stage, false));
         MCOSB_TRY(mark(MCOSB_STAGE_ERRORS, true));
-        MCOSB_TRY(mcosb_dev_errors(ctx, W, dw, d_ideal + (size_t)o * N, 0, plan->error_kind, derr + o,
-                                   plan->n_optimizers));
+        MCOSB_TRY(mcosb_dev_errors(ctx, W, dw, d_ideal + (size_t)o * N, 0, rp.nk, rp.kinds, derr + (size_t)o * rp.nk,
+                                   plan->n_optimizers * rp.nk));
         MCOSB_TRY(mark(MCOSB_STAGE_ERRORS, false));
     }
     return MCOSB_OK;
@@ -99,6 +132,8 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
         if (plan->optimizers[o] < 0 || plan->optimizers[o] > 3) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown optimizer");
     const size_t N = ctx->N;
     const int nopt = plan->n_optimizers;
+    RunPlan rp;
+    MCOSB_TRY(resolve_plan(ctx, plan, rp));
     for (int i = 0; i < MCOSB_N_STAGES; ++i) ctx->stage_ms[i] = 0.0;
     if (S == 0) return MCOSB_OK;
 
@@ -108,7 +143,10 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     Staging st(ctx);
     double* derr;
     int* dstatus;
-    MCOSB_TRY(st.out(err, (size_t)S * nopt, SL_ERR, &derr));
+    MCOSB_TRY(st.out(err, (size_t)S * nopt * rp.nk, SL_ERR, &derr));
+    bool uses_rp = false;
+    for (int o = 0; o < nopt; ++o) uses_rp |= plan->optimizers[o] == MCOSB_OPT_RISK_PARITY;
+    if (uses_rp && plan->risk_budget) MCOSB_TRY(st.in(plan->risk_budget, N, SL_STAGE_IN0, &rp.d_budget));
     if (status) MCOSB_TRY(st.out(status, (size_t)S, SL_STATUS, &dstatus));
     else MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, (size_t)S, &dstatus));
     MCOSB_CUDA(ctx, cudaMemsetAsync(dstatus, 0, (size_t)S * sizeof(int), ctx->stream));
@@ -122,7 +160,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     char key[160];
     snprintf(key, sizeof key, "%d|%d,%d,%d,%d|%.17g|%d|%d", nopt, plan->optimizers[0], plan->optimizers[1],
              plan->optimizers[2], plan->optimizers[3], plan->risk_free_rate, plan->nco_max_clusters, plan->nco_trials);
-    if (ctx->ideal_key != key) {
+    if (ctx->ideal_key != key || rp.d_budget) {   // a custom risk budget is not part of the key: recompute
         ctx->ideal_key.clear();
         MCOSB_CUDA(ctx, cudaMemsetAsync(d_ideal_status, 0, sizeof(int), ctx->stream));
         for (int o = 0; o < nopt; ++o) {
@@ -133,12 +171,12 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
             else if (kind == MCOSB_OPT_HRP)
                 MCOSB_TRY(mcosb_dev_hrp(ctx, 1, ctx->d_cov, wi, nullptr, nullptr, d_ideal_status));
             else if (kind == MCOSB_OPT_RISK_PARITY)
-                MCOSB_TRY(mcosb_dev_risk_parity(ctx, 1, ctx->d_cov, nullptr, wi, nullptr, d_ideal_status));
+                MCOSB_TRY(mcosb_dev_risk_parity(ctx, 1, ctx->d_cov, rp.d_budget, wi, nullptr, d_ideal_status));
             else
                 MCOSB_TRY(mcosb_dev_nco(ctx, 1, ctx->d_mu, ctx->d_cov, plan->nco_max_clusters, plan->nco_trials, nullptr, wi,
                                         nullptr, d_ideal_status));
         }
-        ctx->ideal_key = key;
+        if (!rp.d_budget) ctx->ideal_key = key;
     }
 
     const double t_ideal = now();
@@ -157,6 +195,12 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
         const size_t free_b = ctx->mem_budget > held ? ctx->mem_budget - held : 0;
         // per simulation: cov + denoise work matrix + HRP D and E (4 N^2), inverse-iteration scratch, small vectors
         size_t per_sim = (5 * N * N + 6 * N * 16 + 16 * N) * sizeof(double);
+        for (int o = 0; o < nopt; ++o)
+            if (plan->optimizers[o] == MCOSB_OPT_NCO) {   // NCO: cluster-block work matrix, centres when they spill to HBM
+                const size_t mk = plan->nco_max_clusters > 0 ? (size_t)plan->nco_max_clusters : N / 2;
+                per_sim += (N * N + 4 * N + (2 * mk * N * sizeof(double) > 200000 ? 2 * mk * N : 0)) * sizeof(double);
+                break;
+            }
         size_t budget = (free_b + held) / 2;
         size_t fixed = 2 * RUN_CHUNK_BYTES + ((size_t)1 << 28);  // X + Z chunk buffers
         size_t w = budget > fixed ? (budget - fixed) / per_sim : 1;
@@ -169,7 +213,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     int rc = MCOSB_OK;
     for (int s0 = 0; s0 < S && rc == MCOSB_OK; s0 += wave) {
         const int W = std::min(wave, S - s0);
-        rc = mcosb_run_wave(ctx, plan, sim_id0 + s0, W, d_ideal, derr + (size_t)s0 * nopt, dstatus + s0, marks);
+        rc = mcosb_run_wave(ctx, plan, rp, sim_id0 + s0, W, d_ideal, derr + (size_t)s0 * nopt * rp.nk, dstatus + s0, marks);
     }
     if (rc == MCOSB_OK) rc = st.finish();
     const double t_launched = now();
@@ -190,6 +234,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     if (trace)
         fprintf(stderr, "mcosb_run host ms: ideal-launch %.2f memgetinfo %.2f wave-launch %.2f sync-wait %.2f tail %.2f\n",
                 t_ideal - t_start, t_mem - t_ideal, t_launched - t_mem, t_synced - t_launched, now() - t_synced);
+    ideal_status &= ~MCOSB_ST_NO_EXCESS;   // informational: the Markowitz vertex allocation is defined (markowitz.cu)
     if (ideal_status) {
         char buf[128];
         snprintf(buf, sizeof buf, "ideal allocation on the true (mu, cov) failed with status bits %d", ideal_status);

@@ -1,7 +1,7 @@
 // Two-stage tridiagonalisation (successive band reduction): shared constants and launchers.
 //   stage 1  sy2sb.cu   dense symmetric -> band of half bandwidth SBR_B (blocked Householder, DMMA)
 //   stage 2  sb2st.cu   band -> tridiagonal (bulge chasing in shared memory), reflectors kept for the eigenvectors
-//   back     sbback.cu  x = Q1 Q2 y for the signal eigenvectors
+//   back     q2back_kernel (sb2st.cu) + backtransform_kernel (eigvec3.cu): x = Q1 Q2 y for the signal eigenvectors
 #pragma once
 #include "common.cuh"
 

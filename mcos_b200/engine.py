@@ -243,16 +243,27 @@ class Engine:
         self._check(self.lib.mcosb_errors(self.h, s, pw, pws, batched, kind, pe))
         return err
 
+    def errors_multi(self, w, w_star, kinds):
+        """err[S, len(kinds)]: several estimators from one pass over the weights (column k bit-equal to errors(kinds[k]))."""
+        s = w.shape[0]
+        tt = _is_torch(w)
+        kw, pw = self._in(w, (s, self.N))
+        batched = int(np.prod(tuple(w_star.shape)) == s * self.N and not (s == 1 and len(tuple(w_star.shape)) == 1))
+        kws, pws = self._in(w_star, (s, self.N) if batched else (self.N,))
+        kk = (ctypes.c_int * len(kinds))(*[int(k) for k in kinds])
+        err, pe = self._out(tt, (s, len(kinds)))
+        self._check(self.lib.mcosb_errors_multi(self.h, s, pw, pws, batched, len(kinds), kk, pe))
+        return err
+
     def run(self, plan: Plan, n_sims, sim_id0=0, out_torch=False):
-        err, pe = self._out(out_torch, (n_sims, plan.n_optimizers))
+        shape = (n_sims, plan.n_optimizers, plan.n_error_kinds) if plan.n_error_kinds else (n_sims, plan.n_optimizers)
+        err, pe = self._out(out_torch, shape)
         st, ps = self._out(out_torch, (n_sims,), np.int32)
         rc = self.lib.mcosb_run(self.h, ctypes.byref(plan), ctypes.c_uint64(sim_id0), n_sims, pe, ps)
         if rc == _lib.ERR_IDEAL:  # optimizer.allocate(true mu, true cov) raises in the reference (mcos.py:30)
             bits = int((self.lib.mcosb_last_error(self.h) or b"0").decode().split()[-1])
             if bits & _lib.ST_HRP_SUM:
                 raise ValueError("Portfolio allocations don't sum to 1.")
-            if bits & _lib.ST_NO_EXCESS:
-                raise ValueError("no asset has an expected return above the risk-free rate")
         self._check(rc)
         return err, st
 

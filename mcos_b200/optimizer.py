@@ -37,10 +37,10 @@ class MarkowitzOptimizer(AbstractOptimizer):
         self.device = device
 
     def allocate(self, mu: np.array, cov: np.array) -> np.array:
-        w, info = self.allocate_batch(mu, cov, return_details=True)
-        if info["status"][0] & _lib.ST_NO_EXCESS:
-            raise ValueError("no asset has an expected return above the risk-free rate")
-        return w[0]
+        """When no asset beats the risk-free rate the QP reformulation does not apply; the stated problem's maximum is
+        then the single asset with the best stand-alone Sharpe ratio, which is what is returned (status NO_EXCESS; the
+        reference's SLSQP also stops at a vertex there, a local one)."""
+        return self.allocate_batch(mu, cov)[0]
 
     def allocate_batch(self, mu, cov, clean: bool = True, return_details: bool = False):
         mu, cov, _ = _batch(mu, cov)

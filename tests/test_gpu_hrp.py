@@ -122,6 +122,55 @@ def test_hrp_ties_take_the_fallback():
     _check(cov, w, info, 1)
 
 
+def test_hrp_near_ties_on_the_kernel_take_the_fallback_and_match_scipy():
+    """Near-ties, not exact ties: one covariance entry of the tie-ridden block-diagonal truth is moved by 1..4 ulp, so
+    distances that were equal now differ in the last bits -- far inside the guard's error bound.  The fast pass must
+    flag every such simulation (it cannot know which way scipy's rounded distances fall) and the exact path must then
+    reproduce scipy's linkage bit for bit.  (tests/test_hrp_guard_cpu.py checks the same property on the numpy
+    restatement of the guard; this is the kernel.)"""
+    n = 100
+    mu, cov = block_diagonal_truth(n)
+    corr = cov / np.sqrt(np.outer(np.diag(cov), np.diag(cov)))
+    rng = np.random.RandomState(5)
+    covs = []
+    for k in range(12):
+        c = cov.copy()
+        while True:
+            i, j = rng.randint(0, n, 2)
+            if i != j and corr[i, j] > 0.25:          # same block
+                break
+        v = c[i, j]
+        for _ in range(k % 4 + 1):
+            v = np.nextafter(v, np.inf if k % 2 else -np.inf)
+        c[i, j] = c[j, i] = v
+        covs.append(c)
+    covs = np.stack(covs)
+    eng = Engine(n, 10)
+    eng.hrp_fallback_count()
+    w, info = eng.hrp(covs)
+    assert eng.hrp_fallback_count() == len(covs)
+    for i in range(len(covs)):
+        _check(covs[i], w, info, i)
+    # sampled covariances with ONE near-tie planted: two assets made exchangeable up to a few ulp
+    t = 200
+    x = rng.multivariate_normal(mu, cov, size=t)
+    x[:, 7] = x[:, 3]                                     # asset 7 = asset 3: exact ties in every distance to them
+    base = np.cov(x, rowvar=False)
+    planted = []
+    for k in range(4):
+        c = base.copy()
+        v = c[7, 11]
+        for _ in range(k + 1):
+            v = np.nextafter(v, np.inf)
+        c[7, 11] = c[11, 7] = v                           # d(7, .) and d(3, .) now differ by ulps
+        planted.append(c)
+    planted = np.stack(planted)
+    w2, info2 = eng.hrp(planted)
+    assert eng.hrp_fallback_count() == len(planted)
+    for i in range(len(planted)):
+        _check(planted[i], w2, info2, i)
+
+
 def test_device_tensors_are_ordered_with_torch_work():
     """Device tensors in and out: nothing synchronises with the host, so the kernels must run on the stream the caller's
     torch work is on.  (torch's default stream has handle 0, which mcosb_set_stream reads as "own stream"; the engine

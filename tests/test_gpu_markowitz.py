@@ -6,6 +6,7 @@ import pytest
 from numpy.testing import assert_allclose
 
 import oracle
+import mcos_b200 as mb
 from conftest import run_cases
 from mcos_b200 import _lib
 from mcos_b200.engine import Engine
@@ -70,13 +71,30 @@ def test_markowitz_vs_exact_oracle(n, t, nsim):
 
 
 def test_markowitz_no_excess_return_is_flagged():
-    """All mu_i <= rf: the max-Sharpe transformation does not apply; flagged per simulation, batch not aborted."""
+    """All mu_i <= rf: the max-Sharpe QP does not apply.  The stated problem (PyPortfolioOpt 0.5.2 negative_sharpe on the
+    simplex) then has its maximum at a vertex: the asset with the largest (least negative) stand-alone Sharpe ratio.
+    The simulation is flagged, gets that allocation, and the batch is not aborted.  The reference's SLSQP run stops at a
+    vertex too -- never a better one."""
     mu, cov = block_diagonal_truth(20, n_blocks=2)
     eng = Engine(20, 10)
-    mus = np.stack([mu, np.full(20, 0.01)])
-    w, info = eng.markowitz(mus, np.stack([cov, cov]))
-    assert info["status"][0] == 0 and info["status"][1] & _lib.ST_NO_EXCESS
-    assert np.isnan(w[1]).all() and abs(w[0].sum() - 1) < 1e-4
+    low = mu / 252.0
+    assert (low < 0.02).all()
+    mus = np.stack([mu, low, np.full(20, 0.01)])
+    w, info = eng.markowitz(mus, np.stack([cov, cov, cov]))
+    assert info["status"][0] == 0 and (info["status"][1:] & _lib.ST_NO_EXCESS).all()
+    assert abs(w[0].sum() - 1) < 1e-4
+    sd = np.sqrt(np.diag(cov))
+    for k, m in ((1, low), (2, np.full(20, 0.01))):
+        best = int(np.argmax((m - 0.02) / sd))
+        want = np.zeros(20)
+        want[best] = 1.0
+        assert np.array_equal(w[k], want)
+        ref, _ = oracle.markowitz_slsqp(m, cov)          # the reference's own answer: a vertex, objective no better
+        assert np.sort(ref)[-1] > 1 - 1e-6
+        sharpe = lambda x: (x @ m - 0.02) / np.sqrt(x @ cov @ x)
+        assert sharpe(w[k]) >= sharpe(ref) - 1e-12
+    # and through the class API: no exception (the reference does not raise here either)
+    assert np.array_equal(mb.MarkowitzOptimizer().allocate(low, cov), w[1])
 
 
 def test_markowitz_mu_as_column_vector(stock):

@@ -74,10 +74,14 @@ def test_empty_batches_and_bad_arguments():
         Engine(0, 5)
 
 
-def test_hrp_sum_check_and_markowitz_no_excess_raise_like_the_reference():
+def test_truth_below_the_risk_free_rate_runs_and_is_reported():
+    """A truth on a daily return scale (every mu_i < rf = 0.02): the reference hands Markowitz to SLSQP and carries on;
+    here every simulation gets the best-vertex allocation, the run completes, and the condition is reported."""
     mu, cov = block_diagonal_truth(20, n_blocks=2)
-    with pytest.raises(ValueError):
-        mb.MarkowitzOptimizer().allocate(np.full(20, 0.001), cov)   # nothing above the risk-free rate
-    sim = mb.MuCovObservationSimulator(np.full(20, 0.001), cov, 50)
-    with pytest.raises(ValueError):
-        mb.simulate_optimizations(sim, 4, [mb.MarkowitzOptimizer()], mb.VarianceErrorEstimator(), [])
+    sim = mb.MuCovObservationSimulator(mu / 252.0, cov / 252.0, 50)
+    with pytest.warns(RuntimeWarning, match="NO_EXCESS"):
+        errs, status = mb.simulate_errors(sim, 8, [mb.MarkowitzOptimizer(), mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [])
+    assert np.isfinite(errs).all() and (status & _lib.ST_NO_EXCESS).all()
+    assert mb.status_counts(status) == {"NO_EXCESS": 8}
+    tab = mb.summarize_errors(errs, [mb.MarkowitzOptimizer(), mb.HRPOptimizer()], status=status)
+    assert (tab["n_flagged"] == 8).all()

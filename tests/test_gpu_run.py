@@ -126,18 +126,129 @@ def test_from_price_history(stock):
     assert list(df.index) == ["markowitz", "HRP"] and np.isfinite(df.values).all()
 
 
-def test_unknown_plugin_types_raise():
-    mu, cov = block_diagonal_truth(20, n_blocks=2)
-    sim = mb.MuCovObservationSimulator(mu, cov, 30)
+def test_user_plugins_run_on_the_host_around_the_gpu_stages():
+    """The reference exists to compare arbitrary AbstractOptimizer / AbstractCovarianceTransformer implementations
+    (mcos/mcos.py:22-33 calls whatever it is given).  A plugin type the engine has no kernel for is called on the host
+    once per simulation with the reference's arguments; the built-in plugins around it stay batched on the GPU."""
+    n, t, s = 40, 90, 10
+    mu, cov = block_diagonal_truth(n, n_blocks=4)
+    sim = mb.MuCovObservationSimulator(mu, cov, t, seed=4)
+    calls = {"alloc": 0, "transform": 0, "estimate": 0}
 
-    class MyOpt(mb.AbstractOptimizer):
-        name = "mine"
+    class InverseVariance(mb.AbstractOptimizer):
+        name = "IVP"
 
         def allocate(self, mu, cov):
-            return np.ones(len(cov)) / len(cov)
+            calls["alloc"] += 1
+            assert np.asarray(cov).shape == (n, n)
+            ivp = 1.0 / np.diag(cov)
+            return ivp / ivp.sum()
 
-    with pytest.raises(TypeError):
-        mb.simulate_optimizations(sim, 4, [MyOpt()], mb.VarianceErrorEstimator(), [])
+    class HalfShrink(mb.AbstractCovarianceTransformer):
+        def transform(self, cov, n_observations):
+            calls["transform"] += 1
+            assert n_observations == t
+            return 0.5 * cov + 0.5 * np.diag(np.diag(cov))
+
+    class L1Error(mb.AbstractErrorEstimator):
+        def estimate(self, mu, cov, allocation, optimal_allocation):
+            calls["estimate"] += 1
+            return float(np.abs(optimal_allocation - allocation).sum())
+
+    # (1) user optimizer next to a built-in one, built-in transformer and estimator
+    opts = [InverseVariance(), mb.HRPOptimizer()]
+    errs, status = mb.simulate_errors(sim, s, opts, mb.VarianceErrorEstimator(), [mb.DeNoiserCovarianceTransformer()])
+    assert errs.shape == (s, 2) and (status == 0).all() and calls["alloc"] == s + 1      # + the ideal allocation
+    fused, _ = mb.simulate_errors(sim, s, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [mb.DeNoiserCovarianceTransformer()])
+    assert np.array_equal(errs[:, 1], fused[:, 0])                  # the built-in column is what the fused loop gives
+    eng = get_engine(n, t, 0, 4)
+    x = eng.sample(s, 0)
+    _, cov_hat, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
+    cov_dn, _ = eng.denoise(cov_hat, t)
+    ideal = InverseVariance().allocate(mu, cov)
+    want = [oracle.err_variance(mu, cov, InverseVariance().allocate(None, c), ideal) for c in cov_dn]
+    assert_allclose(errs[:, 0], want, rtol=1e-12, atol=1e-18)
+    # (2) user transformer between two built-in ones, user estimator, a list of estimators
+    trs = [mb.DetoneCovarianceTransformer(1), HalfShrink(), mb.DeNoiserCovarianceTransformer()]
+    e3, st3 = mb.simulate_errors(sim, s, [mb.HRPOptimizer(), mb.MarkowitzOptimizer()], [L1Error(), mb.VarianceErrorEstimator()], trs)
+    assert e3.shape == (s, 2, 2) and calls["transform"] == s and calls["estimate"] == 2 * s
+    c1, _ = eng.detone(cov_hat, 1)
+    c2 = np.stack([HalfShrink().transform(c, t) for c in c1])
+    c3, _ = eng.denoise(c2, t)
+    wh, _ = eng.hrp(c3)
+    ih, _ = eng.hrp(cov[None])
+    assert_allclose(e3[:, 0, 0], np.abs(ih[0] - wh).sum(1), rtol=1e-13)
+    assert np.array_equal(e3[:, 0, 1], eng.errors(wh, ih[0], _lib.ERR_VARIANCE))
+    # (3) a subclass that overrides nothing stays on the fused path; the table has the reference's layout
+    class MyHRP(mb.HRPOptimizer):
+        pass
+    df = mb.simulate_optimizations(sim, s, [MyHRP(), InverseVariance()], mb.VarianceErrorEstimator(), [])
+    assert list(df.index) == ["HRP", "IVP"] and list(df.columns) == ["mean", "stdev"]
+    # (4) a user-defined simulator (global numpy RNG, as the reference's own classes)
+    class NumpySimulator(mb.AbstractObservationSimulator):
+        def __init__(self, mu, cov, n_observations):
+            self.mu, self.cov, self.n_observations = mu, cov, n_observations
+
+        def simulate(self):
+            x = np.random.multivariate_normal(self.mu, self.cov, size=self.n_observations)
+            return x.mean(axis=0).reshape(-1, 1), np.cov(x, rowvar=False)
+
+    np.random.seed(3)
+    e4, _ = mb.simulate_errors(NumpySimulator(mu, cov, t), 5, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [])
+    np.random.seed(3)
+    tab = oracle.simulate_optimizations(mu, cov, t, 5, simulator="mucov", optimizers=("HRP",), estimator="variance",
+                                        return_samples=True)[1]
+    assert_allclose(e4[:, 0], np.ravel(tab["HRP"]), rtol=1e-9)
+
+
+def test_more_than_four_optimizers_and_risk_budget_in_the_fused_loop():
+    """Five optimizers take two passes over the same simulations (Philox draws are keyed by id); a RiskParityOptimizer
+    with a custom target_risk (optimizer.py:295-309) travels through the plan."""
+    n, t, s = 40, 90, 9
+    mu, cov = block_diagonal_truth(n, n_blocks=4)
+    sim = mb.MuCovLedoitWolfObservationSimulator(mu, cov, t, seed=8)
+    budget = np.linspace(1.0, 2.0, n)
+    budget /= budget.sum()
+    opts = [mb.MarkowitzOptimizer(), mb.HRPOptimizer(), mb.NCOOptimizer(5), mb.RiskParityOptimizer(),
+            mb.RiskParityOptimizer(budget)]
+    errs, st = mb.simulate_errors(sim, s, opts, mb.VarianceErrorEstimator(), [mb.DeNoiserCovarianceTransformer()])
+    assert errs.shape == (s, 5)
+    first4, _ = mb.simulate_errors(sim, s, opts[:4], mb.VarianceErrorEstimator(), [mb.DeNoiserCovarianceTransformer()])
+    assert np.array_equal(errs[:, :4], first4)
+    eng = get_engine(n, t, 0, 8)
+    x = eng.sample(s, 0)
+    _, cov_hat, _ = eng.moments(x, _lib.MOMENTS_LEDOIT_WOLF)
+    cov_dn, _ = eng.denoise(cov_hat, t)
+    w, _ = eng.risk_parity(cov_dn, budget)
+    iw, _ = eng.risk_parity(cov[None], budget)
+    assert np.array_equal(errs[:, 4], eng.errors(w, iw[0], _lib.ERR_VARIANCE))
+    assert not np.array_equal(errs[:, 4], errs[:, 3])
+
+
+def test_transformer_lists_in_any_order():
+    """mcos.py:25-26 applies the transformer list in order; [Detone, DeNoiser] and [DeNoiser, Detone, DeNoiser] go
+    through the fused loop and equal the stage-by-stage result bit for bit."""
+    n, t, s = 60, 150, 7
+    mu, cov = block_diagonal_truth(n, n_blocks=6)
+    sim = mb.MuCovObservationSimulator(mu, cov, t, seed=6)
+    eng = get_engine(n, t, 0, 6)
+    eng.ensure_truth(mu, cov)
+    x = eng.sample(s, 0)
+    _, cov_hat, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
+    ih, _ = eng.hrp(cov[None])
+    for trs, stages in (([mb.DetoneCovarianceTransformer(1), mb.DeNoiserCovarianceTransformer()], "TD"),
+                        ([mb.DeNoiserCovarianceTransformer(), mb.DetoneCovarianceTransformer(2), mb.DeNoiserCovarianceTransformer(0.3)], "DtD")):
+        errs, _ = mb.simulate_errors(sim, s, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), trs)
+        c = cov_hat
+        for tr in trs:
+            c = tr.transform_batch(c, t) if isinstance(tr, mb.DeNoiserCovarianceTransformer) else tr.transform_batch(c)
+        wh, _ = eng.hrp(c)
+        assert np.array_equal(errs[:, 0], eng.errors(wh, ih[0], _lib.ERR_VARIANCE)), stages
+        # and the oracle, same order
+        o = cov_hat[0]
+        for tr in trs:
+            o = oracle.denoise(o, t, tr.bandwidth) if isinstance(tr, mb.DeNoiserCovarianceTransformer) else oracle.detone(o, tr.n_remove)
+        assert_allclose(c[0], o, rtol=1e-6, atol=1e-12)
 
 
 @pytest.mark.gpu

@@ -62,28 +62,60 @@ def test_shard_range_partitions_ids():
 
 
 def test_build_plan_maps_plugins_and_rejects_unknown_types():
+    import ctypes
     import mcos_b200 as mb
     from mcos_b200 import _lib
     mu, cov = np.zeros(4), np.eye(4)
     sim = mb.MuCovLedoitWolfObservationSimulator(mu, cov, 10)
     plan = mb.build_plan(sim, [mb.MarkowitzOptimizer(), mb.HRPOptimizer(), mb.NCOOptimizer(5, 3)],
                          mb.SharpeRatioErrorEstimator(), [mb.DeNoiserCovarianceTransformer(0.3), mb.DetoneCovarianceTransformer(0)])
-    assert plan.moments_kind == _lib.MOMENTS_LEDOIT_WOLF and plan.denoise == 1 and plan.bandwidth == 0.3
+    assert plan.moments_kind == _lib.MOMENTS_LEDOIT_WOLF
+    assert plan.n_transformers == 1 and plan.transformer_kind[0] == _lib.TR_DENOISE and plan.transformer_arg[0] == 0.3
     assert list(plan.optimizers)[:3] == [_lib.OPT_MARKOWITZ, _lib.OPT_HRP, _lib.OPT_NCO] and plan.n_optimizers == 3
-    assert plan.error_kind == _lib.ERR_SHARPE and plan.nco_max_clusters == 5 and plan.nco_trials == 3
-    assert plan.risk_free_rate == 0.02
+    assert plan.error_kind == _lib.ERR_SHARPE and plan.n_error_kinds == 0
+    assert plan.nco_max_clusters == 5 and plan.nco_trials == 3 and plan.risk_free_rate == 0.02 and not plan.risk_budget
     assert list(mb.build_plan(sim, [mb.RiskParityOptimizer()], mb.VarianceErrorEstimator(), []).optimizers)[0] == \
         _lib.OPT_RISK_PARITY
-    with pytest.raises(TypeError):   # custom budgets only through the optimizer object itself
-        mb.build_plan(sim, [mb.RiskParityOptimizer(np.full(4, .25))], mb.VarianceErrorEstimator(), [])
+    # RiskParityOptimizer(target_risk) (optimizer.py:295-309): the budget travels with the plan
+    budget = np.array([.1, .2, .3, .4])
+    prp = mb.build_plan(sim, [mb.RiskParityOptimizer(budget)], mb.VarianceErrorEstimator(), [])
+    got = np.ctypeslib.as_array(ctypes.cast(prp.risk_budget, ctypes.POINTER(ctypes.c_double)), shape=(4,))
+    assert np.array_equal(got, budget)
+    # any list of the built-in transformers, in order (mcos.py:25-26)
     plan2 = mb.build_plan(sim, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(),
-                          [mb.DeNoiserCovarianceTransformer(), mb.DetoneCovarianceTransformer(2)])
-    assert plan2.denoise == 1 and plan2.detone_n_remove == 2
-    with pytest.raises(TypeError):   # the fused plan applies the DeNoiser first
-        mb.build_plan(sim, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(),
-                      [mb.DetoneCovarianceTransformer(1), mb.DeNoiserCovarianceTransformer()])
+                          [mb.DetoneCovarianceTransformer(1), mb.DeNoiserCovarianceTransformer(), mb.DetoneCovarianceTransformer(2)])
+    assert plan2.n_transformers == 3 and list(plan2.transformer_kind)[:3] == [_lib.TR_DETONE, _lib.TR_DENOISE, _lib.TR_DETONE]
+    assert list(plan2.transformer_arg)[:3] == [1.0, 0.25, 2.0]
+    # several estimators in one pass
+    plan3 = mb.build_plan(sim, [mb.HRPOptimizer()],
+                          [mb.ExpectedOutcomeErrorEstimator(), mb.VarianceErrorEstimator(), mb.SharpeRatioErrorEstimator()], [])
+    assert plan3.n_error_kinds == 3 and list(plan3.error_kinds) == [_lib.ERR_EXPECTED_OUTCOME, _lib.ERR_VARIANCE, _lib.ERR_SHARPE]
+    # the struct the header declares: 144 bytes, the pointer last
+    assert ctypes.sizeof(_lib.Plan) == 144 and _lib.Plan.risk_budget.offset == 136
+
+    # subclasses that keep the behaviour method stay on the GPU; user plugins and overriding subclasses have no GPU stage
+    class Tuned(mb.HRPOptimizer):
+        pass
+
+    class Mine(mb.HRPOptimizer):
+        def allocate(self, mu, cov):
+            return np.full(len(cov), 1.0 / len(cov))
+
+    assert mb.build_plan(sim, [Tuned()], mb.VarianceErrorEstimator(), []).optimizers[0] == _lib.OPT_HRP
+    with pytest.raises(TypeError):
+        mb.build_plan(sim, [Mine()], mb.VarianceErrorEstimator(), [])
     with pytest.raises(TypeError):
         mb.build_plan(object(), [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [])
+
+
+def test_plan_struct_matches_the_header():
+    """The ctypes Plan mirrors `struct mcosb_plan` of include/mcosb.h field for field (names and order)."""
+    from mcos_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "mcosb.h")).read()
+    body = text[text.index("typedef struct mcosb_plan {"):text.index("} mcosb_plan;")]
+    import re
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|double)\*?\s+(\w+)(?:\[[^\]]+\])?;", body, flags=re.M)
+    assert names == [f[0] for f in _lib.Plan._fields_], names
 
 
 def test_reference_api_surface():
@@ -132,6 +164,9 @@ local = np.stack([np.arange(lo, hi, dtype=float), -np.arange(lo, hi, dtype=float
 full = gather_errors(local, n)
 want = np.stack([np.arange(n, dtype=float), -np.arange(n, dtype=float)], axis=1)
 assert np.array_equal(full, want), full
+# 3-D blocks (several estimators) travel the same way
+full3 = gather_errors(local.reshape(hi - lo, 1, 2), n)
+assert np.array_equal(full3, want.reshape(n, 1, 2))
 dist.destroy_process_group()
 print("ok", rank)
 """
