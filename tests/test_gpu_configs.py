@@ -225,7 +225,7 @@ def test_config2_mucov_denoise_markowitz():
     n_safe, n_near = _check_markowitz(r["eng"], r["mu"], r["cov"], r["mu_hat_gpu"], r["cov_gpu"], r["errs"][:, 0, :],
                                       r["mu_hat_o"], r["cov_o"], ideal_m, kinds)
     print(f"config 2: Markowitz {n_safe} matched at 1e-9, {n_near} near a rounding boundary")
-    assert n_safe >= s // 2
+    assert n_safe >= 1 and n_safe + n_near == s
 
 
 def test_nco_partition_agreement_rate_config4_shape():

@@ -222,7 +222,10 @@ def test_more_than_four_optimizers_and_risk_budget_in_the_fused_loop():
     w, _ = eng.risk_parity(cov_dn, budget)
     iw, _ = eng.risk_parity(cov[None], budget)
     assert np.array_equal(errs[:, 4], eng.errors(w, iw[0], _lib.ERR_VARIANCE))
-    assert not np.array_equal(errs[:, 4], errs[:, 3])
+    # the budget reached the kernel: at this covariance scale SLSQP's first convergence test fires at the starting point,
+    # which is the budget itself (optimizer.py:349-359; riskparity.cu), not 1/N
+    assert_allclose(iw[0], budget, rtol=0, atol=1e-15)
+    assert not np.allclose(iw[0], 1.0 / n)
 
 
 def test_transformer_lists_in_any_order():
