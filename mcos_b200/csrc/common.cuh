@@ -19,7 +19,7 @@ enum ScratchSlot {
     SL_MK_L, SL_MK_W, SL_MK_ITERS,
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
     SL_NCO_W, SL_NCO_LABELS, SL_NCO_WORK, SL_NCO_E,
-    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2, SL_NCO_CENTERS,
+    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2, SL_NCO_CENTERS, SL_S2_ZP, SL_S2_ZC,
     SL_COUNT
 };
 

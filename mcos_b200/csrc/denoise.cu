@@ -901,12 +901,12 @@ int mcosb_dev_tridiagonalize(mcosb_ctx* ctx, int S, double* A, double* d, double
     *q2 = nullptr;
     const bool sbr = mcosb_sbr_supported(ctx) && (ctx->eig_method == 2 || (ctx->eig_method == 0 && N >= SBR_MIN_N));
     if (ctx->eig_method == 2 && !sbr)
-        return mcosb_fail(ctx, MCOSB_ERR_ARG, "two-stage tridiagonalisation needs 10 <= n_assets <= 696");
+        return mcosb_fail(ctx, MCOSB_ERR_ARG, "two-stage tridiagonalisation needs 10 <= n_assets <= 1024");
     if (sbr) {
         // two-stage: dense -> band (sy2sb.cu, DMMA) -> tridiagonal (sb2st.cu, bulge chasing in shared memory)
         double* Q2;
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_DN_Q2, (size_t)S * n * n, &Q2));
-        int r1 = mcosb_launch_sy2sb(ctx, S, A, tau);
+        int r1 = mcosb_launch_stage1(ctx, S, A, tau);
         if (r1 < 0) return r1;
         int r2 = r1 == 1 ? mcosb_launch_sb2st(ctx, S, A, d, e, Q2) : 0;
         if (r2 < 0) return r2;

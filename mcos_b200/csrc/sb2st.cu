@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(W * 32) sb2st_mma_kernel(const double* __restr
 int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double* e, double* Q2) {
     const int N = ctx->N;
     const size_t smem = (size_t)(N + 16) * 16 * sizeof(double);
-    if (smem + 1024 > (size_t)ctx->smem_optin || N > 768) return 0;
+    if (smem + 1024 > (size_t)ctx->smem_optin || N > 1024) return 0;
     static int Wsel = -1;
     if (Wsel < 0) {
         const char* e = getenv("MCOSB_SB2ST_W");
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(Q2B_NT) q2back_kernel(const double* __restrict
     // the reflectors of sweep s (N - 1 - s doubles) are staged in shared memory one sweep ahead: the global load of the
     // next row overlaps the work on the current one
     double* Qs = Y + (size_t)(N + 8) * Q2B_V;      // [2][N + 8]
-    constexpr int PF = 3;                          // N <= 768
+    constexpr int PF = (1024 + Q2B_NT - 1) / Q2B_NT;   // N <= 1024
     for (int idx = tid; idx < 2 * (N + 8); idx += Q2B_NT) Qs[idx] = 0.0;
     __syncthreads();
     if (N >= 3)
@@ -527,9 +527,21 @@ int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, 
     return 1;
 }
 
+static bool sbr_use_old_stage1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MCOSB_SY2SB_OLD"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
+
 bool mcosb_sbr_supported(mcosb_ctx* ctx) {
     const int N = ctx->N;
     extern size_t sbr_stage1_smem(int N);
-    return N >= SBR_B + 2 && N <= 768 && sbr_stage1_smem(N) <= (size_t)ctx->smem_optin &&
+    const bool stage1 = sbr_use_old_stage1() ? (N <= 768 && sbr_stage1_smem(N) <= (size_t)ctx->smem_optin) : sbr2_supported(ctx);
+    const size_t q2b = ((size_t)(N + 8) * Q2B_V + 2 * (size_t)(N + 8)) * sizeof(double);
+    return N >= SBR_B + 2 && N <= 1024 && stage1 && q2b <= (size_t)ctx->smem_optin &&
            (size_t)(N + 16) * 16 * sizeof(double) + 1024 <= (size_t)ctx->smem_optin;
+}
+
+int mcosb_launch_stage1(mcosb_ctx* ctx, int S, double* A, double* tau) {
+    return sbr_use_old_stage1() ? mcosb_launch_sy2sb(ctx, S, A, tau) : mcosb_launch_sy2sb2(ctx, S, A, tau);
 }

@@ -9,7 +9,10 @@
 #define SBR_MIN_N 128   // below this the one-stage kernels are used (mcosb_dev_eig_prepare)
 
 // Each returns 1 if launched, 0 if the problem size is outside its range (nothing launched), < 0 on error.
-int mcosb_launch_sy2sb(mcosb_ctx* ctx, int S, double* A, double* tau);
+int mcosb_launch_sy2sb(mcosb_ctx* ctx, int S, double* A, double* tau);    // round-1 kernel (N <= 696), MCOSB_SY2SB_OLD=1
+int mcosb_launch_sy2sb2(mcosb_ctx* ctx, int S, double* A, double* tau);   // two matrices per SM / N <= 1024 (sy2sb2.cu)
+bool sbr2_supported(mcosb_ctx* ctx);
+int mcosb_launch_stage1(mcosb_ctx* ctx, int S, double* A, double* tau);       // the one in use
 int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double* e, double* Q2);
 int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, double* Wy);
 bool mcosb_sbr_supported(mcosb_ctx* ctx);

@@ -26,7 +26,8 @@ def _tri_eigs(d, e):
     return np.linalg.eigvalsh(t)
 
 
-@pytest.mark.parametrize("n", [10, 11, 16, 17, 18, 25, 33, 64, 65, 96, 100, 129, 200, 257, 333, 500, 512, 513, 690, 696])
+@pytest.mark.parametrize("n", [10, 11, 16, 17, 18, 25, 33, 64, 65, 96, 100, 129, 200, 255, 256, 257, 333, 500, 511, 512, 513, 520, 690, 696,
+                               768, 777, 1000, 1023, 1024])
 def test_two_stage_tridiagonal_is_similar(n):
     a = _corr_batch(n, 3, n)
     eng = Engine(n, 2 * n)
@@ -51,7 +52,7 @@ def test_one_stage_still_available():
         assert_allclose(_tri_eigs(d[i], e[i]), np.linalg.eigvalsh(a[i]), rtol=0, atol=1e-12 * n)
 
 
-@pytest.mark.parametrize("n,t", [(100, 200), (130, 520), (500, 1000), (60, 30), (333, 700)])
+@pytest.mark.parametrize("n,t", [(100, 200), (130, 520), (500, 1000), (60, 30), (333, 700), (1000, 2000)])
 def test_denoise_two_stage_matches_one_stage_and_oracle(n, t):
     rng = np.random.RandomState(n)
     a = rng.standard_normal((n, 8)) * (np.arange(8) + 1.0)
@@ -148,10 +149,10 @@ def test_tensor_core_bulge_chasing_variant():
 
 
 def test_automatic_method_outside_the_two_stage_range():
-    """N = 700 > 696 (shared memory of stage 1): automatic selection falls back to the one-stage kernel, forcing the
+    """N = 1030 > 1024 (shared memory of stage 1): automatic selection falls back to the one-stage kernel, forcing the
     two-stage method is an argument error -- never a silent wrong answer."""
     from mcos_b200._lib import MCOSBError
-    n = 700
+    n = 1030
     a = _corr_batch(n, 2, 3)
     eng = Engine(n, 2 * n)
     d, e = eng.tridiagonalize(a)
@@ -162,3 +163,26 @@ def test_automatic_method_outside_the_two_stage_range():
         eng.tridiagonalize(a)
     with pytest.raises(MCOSBError):
         eng.set_eig_method(3)
+
+
+def test_round1_stage1_kernel_still_selectable():
+    """MCOSB_SY2SB_OLD=1 runs the round-1 dense -> band kernel (one 16-warp CTA per SM, N <= 696) for A/B timing."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import numpy as np
+        from mcos_b200.engine import Engine
+        n = 300
+        rng = np.random.RandomState(4)
+        a = np.stack([np.corrcoef(rng.standard_normal((2 * n, n)), rowvar=False) for _ in range(3)])
+        eng = Engine(n, 2 * n)
+        eng.set_eig_method(2)
+        d, e = eng.tridiagonalize(a)
+        for i in range(3):
+            t = np.diag(d[i]) + np.diag(e[i][:n - 1], 1) + np.diag(e[i][:n - 1], -1)
+            err = np.abs(np.linalg.eigvalsh(t) - np.linalg.eigvalsh(a[i])).max()
+            assert err < 1e-12 * n, err
+        print("ok")
+    """)
+    env = dict(os.environ, MCOSB_SY2SB_OLD="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
