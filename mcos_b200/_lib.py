@@ -7,7 +7,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcosb200.so")
+# MCOSB_LIB_PATH: an alternative build of the same library (timing / ablation variants for A/B runs)
+LIB_PATH = os.environ.get("MCOSB_LIB_PATH") or os.path.join(_HERE, "libmcosb200.so")
 
 N_STAGES = 7
 STAGE_NAMES = ("sample", "moments", "denoise", "markowitz", "hrp", "nco", "errors")

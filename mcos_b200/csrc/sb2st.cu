@@ -527,21 +527,29 @@ int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, 
     return 1;
 }
 
-static bool sbr_use_old_stage1() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("MCOSB_SY2SB_OLD"); v = (e && atoi(e)) ? 1 : 0; }
-    return v == 1;
+// Which dense -> band kernel: the round-1 kernel (sy2sb.cu: one 16-warp CTA per SM, register ring of 2 tiles, one barrier per
+// 32-row block row; N <= 696) or sy2sb2.cu (barrier-free pass with the Z partials in L2, cp.async tile ring, two matrices
+// per SM for small N, N <= 1024).  Measured per matrix on B200 (profiles/sy2sb2_r02.md): N = 400: 10.9 vs 10.8 us,
+// N = 500: 18.4 vs 21.0, N = 600: 35.9 vs 40.0, N = 696: 52.1 vs 75.4 -- removing the barrier and the register ring did not
+// pay (the pass is bound by shared-memory / shuffle issue and DMMA dependency latency, not by the barrier), so the old
+// kernel stays the default wherever it runs and the new one takes N = 697 .. 1024, where the alternative is the one-stage
+// kernel at 527 us per matrix (N = 1000: 183 us).  MCOSB_SY2SB_OLD=0 forces the new kernel everywhere (A/B runs, tests).
+static bool sbr_use_old_stage1(int N) {
+    static int v = -2;
+    if (v == -2) { const char* e = getenv("MCOSB_SY2SB_OLD"); v = e ? (atoi(e) ? 1 : 0) : -1; }
+    if (v >= 0) return v == 1 && N <= 696;
+    return N <= 696;
 }
 
 bool mcosb_sbr_supported(mcosb_ctx* ctx) {
     const int N = ctx->N;
     extern size_t sbr_stage1_smem(int N);
-    const bool stage1 = sbr_use_old_stage1() ? (N <= 768 && sbr_stage1_smem(N) <= (size_t)ctx->smem_optin) : sbr2_supported(ctx);
+    const bool stage1 = sbr_use_old_stage1(N) ? (sbr_stage1_smem(N) <= (size_t)ctx->smem_optin) : sbr2_supported(ctx);
     const size_t q2b = ((size_t)(N + 8) * Q2B_V + 2 * (size_t)(N + 8)) * sizeof(double);
     return N >= SBR_B + 2 && N <= 1024 && stage1 && q2b <= (size_t)ctx->smem_optin &&
            (size_t)(N + 16) * 16 * sizeof(double) + 1024 <= (size_t)ctx->smem_optin;
 }
 
 int mcosb_launch_stage1(mcosb_ctx* ctx, int S, double* A, double* tau) {
-    return sbr_use_old_stage1() ? mcosb_launch_sy2sb(ctx, S, A, tau) : mcosb_launch_sy2sb2(ctx, S, A, tau);
+    return sbr_use_old_stage1(ctx->N) ? mcosb_launch_sy2sb(ctx, S, A, tau) : mcosb_launch_sy2sb2(ctx, S, A, tau);
 }

@@ -13,7 +13,8 @@
 //     sums of Z for every 16-row block row to a per-matrix scratch in global memory (L2-resident: 8 x 8 x N doubles,
 //     rewritten every panel) instead of meeting the other seven warps at a __syncthreads per block row; the W phase folds
 //     the eight partials (fixed order: deterministic) while it reads its row of Z;
-//   * a register ring of 4 tiles (16 x 8 each) per warp instead of 2;
+//   * tiles prefetched with cp.async into thread-private shared-memory slots (4 ahead) instead of a register ring of 2:
+//     no registers, no barrier, and no scoreboard shared with the operand loads of the tile in work;
 //   * N up to 1024 with one 16-warp CTA per SM (two row groups x 8 column classes, the column blocks of a class taken in
 //     two sub-passes of 8 so the column-side accumulators stay at 16 registers): config 5 (N = 1000) no longer falls
 //     back to the one-stage kernel.
@@ -26,7 +27,15 @@
 #include "dmma.cuh"
 #include "sbr.cuh"
 
-#define S2_D 4    // tiles in flight per warp (register ring), a power of two
+#ifndef S2_D
+#define S2_D 2    // register-ring variant (SD == 0): tiles in flight per warp, a power of two
+#endif
+#ifndef S2_VNI_REG
+#define S2_VNI_REG 0   // 1: keep the V_n[rows] fragments of a block row in registers (8 more)
+#endif
+#ifndef S2_MINB
+#define S2_MINB(NW) ((NW) == 8 ? 2 : 1)
+#endif
 
 #ifdef S2_TIMING
 #define S2_TICK(idx) do { if (threadIdx.x == 0) { long long now__ = clock64(); s2_acc[idx] += now__ - s2_last; s2_last = now__; } } while (0)
@@ -85,8 +94,12 @@ __device__ __forceinline__ double s2_rsqrt(double x) {
 
 // NW = 8 RG warps: warp w works on column blocks cb = 8 q + (w & 7) and on the 16-row block rows n = (w >> 3) (mod RG).
 // RPT = rows per thread in the panel phases (ceil(N / threads)); QH = sub-passes of 8 column blocks per class (ceil(N / 512)).
-template <int NW, int RPT, int QH>
-__global__ void __launch_bounds__(NW * 32, (NW == 8 ? 2 : 1))
+// SD > 0: tiles are prefetched with cp.async into thread-private shared-memory slots, SD tiles ahead of their use (each
+// lane copies exactly the 2 x 16 bytes it will read itself: no barrier, no registers held, and -- unlike loads into a
+// register ring -- no scoreboard shared with the LDS / DMMA traffic of the tile being worked on).  SD == 0: register ring of
+// S2_D tiles (the arrangement for N > 640, where shared memory has no room for the slots).
+template <int NW, int RPT, int QH, int SD, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall, double* __restrict__ Zp_all,
               double* __restrict__ Zc_all) {
     constexpr int NT = NW * 32;
@@ -103,6 +116,7 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
     double* M0 = tauS + 8;                    // [8][8]
     double* Mm = M0 + 64;                     // [8][8]
     double* partM = Mm + 64;                  // [NW][64]
+    double* ringS = partM + NW * 64;          // [NW][SD][128]  (SD > 0): lane's pieces at [2 lane] (rows g) and [64 + 2 lane] (rows g + 8)
 
     const int s = blockIdx.x;
     double* A = Aall + (size_t)s * N * N;
@@ -293,13 +307,44 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
             double zc[8][2];
 #pragma unroll
             for (int q = 0; q < 8; ++q) zc[q][0] = zc[q][1] = 0.0;
-            // ring of S2_D tiles in registers; slot (q - qbase) % S2_D holds the next unprocessed fast tile with that residue.
-            // Every load is unconditional (clamped address) and lands directly in the ring: the ring registers are only read
-            // (C input of an out-of-place DMMA) before they are refilled, so ptxas keeps the loads in flight.
+            auto qf_of = [&](int n) -> int { return min(qfast_of(n), qhi_of(n)); };
+            // ---- tile prefetch -----------------------------------------------------------------------------------------------
+            // SD > 0: the warp's fast tiles form one sequence (owned block rows in order, q ascending inside a row); the
+            // producer cursor (pn, pq) runs SD tiles ahead of the consumer, slot = sequence number mod SD, one commit group per
+            // sequence number (empty once the producer has run out), so cp.async.wait_group SD-1 before tile k guarantees group k.
+            double* myslot = ringS + (size_t)w * (SD > 0 ? SD : 1) * 128 + 2 * lane;
+            int pn = wh, pq = qlo;
+            unsigned pseq = 0, cseq = 0;
+            auto issue = [&]() {
+                if (SD > 0) {
+                    if (pn < nbr) {
+                        const double* src = A + (size_t)(R0 + 16 * pn + g) * N + 8 * wc + 2 * t + 64 * pq;
+                        double* dst = myslot + (pseq % (SD > 0 ? SD : 1)) * 128;
+                        cp_async16(dst, src, true);
+                        cp_async16(dst + 64, src + rowstep, true);
+                        if (pq < qf_of(pn)) ++pq;
+                        else {
+                            pn += RG;
+                            pq = qlo;
+                            if (pn < nbr && qf_of(pn) < qlo) pn = nbr;     // only the overhanging last block row: no fast tiles
+                        }
+                    }
+                    cp_async_commit();
+                    ++pseq;
+                }
+            };
+            if (SD > 0) {
+                while (pn < nbr && qf_of(pn) < qlo) pn += RG;              // first owned block row with a fast tile
+#pragma unroll
+                for (int d = 0; d < (SD > 0 ? SD : 1); ++d) issue();
+            }
+            // SD == 0: ring of S2_D tiles in registers; slot (q - qbase) % S2_D holds the next unprocessed fast tile with that
+            // residue.  Every load is unconditional (clamped address) and lands directly in the ring: the ring registers are only
+            // read (C input of an out-of-place DMMA) before they are refilled, so ptxas keeps the loads in flight.
             double ring[S2_D][2][2];
             const double* tile00 = A + (size_t)(R0 + g) * N + 8 * wc + 2 * t;   // tile (0, 0); (n, q): + 16 n N + 64 q
-            {
-                const int qf0 = min(qfast_of(wh), qhi_of(wh));
+            if (SD == 0) {
+                const int qf0 = qf_of(wh);
 #pragma unroll
                 for (int d = 0; d < S2_D; ++d) {
                     const int qd = qlo + ((d - qlo) & (S2_D - 1));
@@ -313,17 +358,26 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
                 const int qfn = (n + RG < nbr) ? min(qfast_of(n + RG), qhi_of(n + RG)) : -1;
                 double* rowbase = A + (size_t)(i0 + g) * N + 8 * wc + 2 * t;
                 const double* nextbase = rowbase + (size_t)16 * RG * N;
-                // slots this block row does not use take their tile of the next block row now
+                // (register ring) slots this block row does not use take their tile of the next block row now
+                if (SD == 0) {
 #pragma unroll
-                for (int d = 0; d < S2_D; ++d) {
-                    const int qd = qlo + ((d - qlo) & (S2_D - 1));
-                    if (qd > qf && qd <= qfn) ring_load(ring[d], nextbase + 64 * qd);
+                    for (int d = 0; d < S2_D; ++d) {
+                        const int qd = qlo + ((d - qlo) & (S2_D - 1));
+                        if (qd > qf && qd <= qfn) ring_load(ring[d], nextbase + 64 * qd);
+                    }
                 }
                 double zi[2][2];
 #pragma unroll
                 for (int rb = 0; rb < 2; ++rb) zi[rb][0] = zi[rb][1] = 0.0;
                 if (qlo <= qhi) {
-                    double av[2][4], vni[2][2];
+                    double av[2][4];
+#if S2_VNI_REG
+                    double vni[2][2];
+#define S2_VNI(rb, hh) vni[rb][hh]
+#else
+                    const double* vnrow = Vn + g * LD + i0 + t;      // V_n[rows] fragments re-read per tile: 8 registers less
+#define S2_VNI(rb, hh) vnrow[8 * (rb) + 4 * (hh)]
+#endif
 #pragma unroll
                     for (int rb = 0; rb < 2; ++rb) {
                         const int i = i0 + 8 * rb + g;
@@ -331,27 +385,40 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
                         av[rb][1] = -Vp[(4 + t) * LD + i];
                         av[rb][2] = -Wp[t * LD + i];
                         av[rb][3] = -Wp[(4 + t) * LD + i];
+#if S2_VNI_REG
                         vni[rb][0] = Vn[g * LD + i0 + 8 * rb + t];
                         vni[rb][1] = Vn[g * LD + i0 + 8 * rb + 4 + t];
+#endif
                     }
                     // ---- tiles entirely below the diagonal -----------------------------------------------------------------
 #pragma unroll
                     for (int ql = 0; ql < 8; ++ql) {
                         const int q = qbase + ql;
                         if (q >= qlo && q <= qf) {
-                            double (&cur)[2][2] = ring[ql % S2_D];
-                            // refill address: same block row if it has a tile q + D, else this slot's tile of the next block row,
-                            // else (nothing left for the slot) the current tile again -- always valid memory
-                            const int q2 = qlo + ((q - qlo) & (S2_D - 1));
-                            const double* refill = (q + S2_D <= qf) ? rowbase + 64 * (q + S2_D)
-                                                                     : ((q2 <= qfn) ? nextbase + 64 * q2 : rowbase + 64 * q);
                             const double bw0 = Wp[cK0 + 64 * q], bw1 = Wp[cK4 + 64 * q];
                             const double bv0 = Vp[cK0 + 64 * q], bv1 = Vp[cK4 + 64 * q];
                             const double2 vnj = *reinterpret_cast<const double2*>(Vn + cVn + 64 * q);
                             double u[2][2];
+                            if (SD > 0) {
+                                cp_async_wait<(SD > 0 ? SD - 1 : 0)>();
+                                const double* slot = myslot + (cseq % (SD > 0 ? SD : 1)) * 128;
+                                const double2 c0 = *reinterpret_cast<const double2*>(slot);
+                                const double2 c1 = *reinterpret_cast<const double2*>(slot + 64);
+                                ++cseq;
+                                dmma_884_oop(u[0][0], u[0][1], av[0][0], bw0, c0.x, c0.y);
+                                dmma_884_oop(u[1][0], u[1][1], av[1][0], bw0, c1.x, c1.y);
+                                issue();
+                            } else {
+                                double (&cur)[2][2] = ring[ql % S2_D];
+                                // refill address: same block row if it has a tile q + D, else this slot's tile of the next block row,
+                                // else (nothing left for the slot) the current tile again -- always valid memory
+                                const int q2 = qlo + ((q - qlo) & (S2_D - 1));
+                                const double* refill = (q + S2_D <= qf) ? rowbase + 64 * (q + S2_D)
+                                                                         : ((q2 <= qfn) ? nextbase + 64 * q2 : rowbase + 64 * q);
 #pragma unroll
-                            for (int rb = 0; rb < 2; ++rb) dmma_884_oop(u[rb][0], u[rb][1], av[rb][0], bw0, cur[rb][0], cur[rb][1]);
-                            ring_load(cur, refill);
+                                for (int rb = 0; rb < 2; ++rb) dmma_884_oop(u[rb][0], u[rb][1], av[rb][0], bw0, cur[rb][0], cur[rb][1]);
+                                ring_load(cur, refill);
+                            }
 #pragma unroll
                             for (int rb = 0; rb < 2; ++rb) dmma_884(u[rb][0], u[rb][1], av[rb][1], bw1);
 #pragma unroll
@@ -374,7 +441,7 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
                                     const int src = 4 * (4 * hh + t) + (g >> 1);
                                     const double e0 = __shfl_sync(0xffffffffu, u[rb][0], src);
                                     const double e1 = __shfl_sync(0xffffffffu, u[rb][1], src);
-                                    dmma_884(zc[ql][0], zc[ql][1], vni[rb][hh], (g & 1) ? e1 : e0);
+                                    dmma_884(zc[ql][0], zc[ql][1], S2_VNI(rb, hh), (g & 1) ? e1 : e0);
                                 }
                             }
                         }
@@ -429,7 +496,7 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
                                     const int src = 4 * (4 * hh + t) + (g >> 1);
                                     const double e0 = __shfl_sync(0xffffffffu, lt[rb][0], src);
                                     const double e1 = __shfl_sync(0xffffffffu, lt[rb][1], src);
-                                    dmma_884(zc[ql][0], zc[ql][1], vni[rb][hh], (g & 1) ? e1 : e0);
+                                    dmma_884(zc[ql][0], zc[ql][1], S2_VNI(rb, hh), (g & 1) ? e1 : e0);
                                 }
                             }
                         }
@@ -569,50 +636,74 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
 
 // LD = 8 (mod 16) keeps the 16-byte fragment loads of the k-major arrays on distinct bank groups (MCOSB_S2_LDMOD for
 // experiments); >= N + 16 so the last 16-row block row may overhang N (those rows hold zeros).
-static int s2_ldmod() {
-    static int m = -1;
-    if (m < 0) {
-        const char* e = getenv("MCOSB_S2_LDMOD");
-        m = e ? (atoi(e) & 15) : 8;
-    }
-    return m;
+static int s2_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 int sbr2_ld(int N) {
+    static const int mod = s2_env("MCOSB_S2_LDMOD", 8) & 15;
     int ld = N + 16;
-    while ((ld & 15) != s2_ldmod()) ++ld;
+    while ((ld & 15) != mod) ++ld;
     return ld;
 }
 static int sbr2_ldz(int N) { return (N + 16 + 7) & ~7; }
-static int sbr2_nw(int N) { return N <= 512 ? 8 : 16; }
+
+// Kernel configuration by problem size: warps per matrix, rows per thread in the panel phases, column sub-passes, depth of
+// the cp.async tile ring (0 = register ring) and matrices per SM.
+struct S2Config { int nw, rpt, qh, sd, minb; };
+static S2Config sbr2_config(int N) {
+    static const int force16 = s2_env("MCOSB_S2_FORCE16", 0);      // A/B: one 16-warp CTA per SM also for small N
+    static const int sd16 = s2_env("MCOSB_S2_SD16", 4);           // ring depth of the 16-warp variant (4 or 6)
+    if (N <= 256 && !force16) return {8, 1, 1, 4, 2};
+    if (N <= 440 && !force16) return {8, 2, 1, 2, 2};
+    if (N <= 512) return {16, 1, 1, sd16 == 6 ? 6 : 4, 1};
+    if (N <= 640) return {16, 2, 2, 4, 1};
+    return {16, 2, 2, 0, 1};
+}
 size_t sbr2_smem(int N) {
-    const int nw = sbr2_nw(N);
-    return ((size_t)24 * sbr2_ld(N) + 2 * nw * 8 + 16 + 64 + 8 + 64 + 64 + nw * 64) * sizeof(double);
+    const S2Config c = sbr2_config(N);
+    return ((size_t)24 * sbr2_ld(N) + 2 * c.nw * 8 + 16 + 64 + 8 + 64 + 64 + c.nw * 64 + (size_t)c.nw * c.sd * 128) * sizeof(double);
 }
 bool sbr2_supported(mcosb_ctx* ctx) {
     const int N = ctx->N;
     return N >= SBR_B + 2 && N <= 1024 && sbr2_smem(N) <= (size_t)ctx->smem_optin;
 }
 
+template <int NW, int RPT, int QH, int SD, int MINB>
+static int s2_launch(mcosb_ctx* ctx, int S, double* A, double* tau, size_t smem, int LD, int LDZ, double* Zp, double* Zc) {
+    static const bool trace = getenv("MCOSB_TRACE") != nullptr;
+    auto kern = sy2sb2_kernel<NW, RPT, QH, SD, MINB>;
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need the whole 228 KB as shared memory: ask for the maximum carve-out explicitly
+    MCOSB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (trace) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        fprintf(stderr, "sy2sb2<%d,%d,%d,%d,%d>: N %d LD %d smem %zu regs %d local %zu -> %d CTAs per SM\n", NW, RPT, QH, SD,
+                MINB, ctx->N, LD, smem, fa.numRegs, (size_t)fa.localSizeBytes, nb);
+    }
+    kern<<<S, NW * 32, smem, ctx->stream>>>(A, ctx->N, LD, LDZ, tau, Zp, Zc);
+    return MCOSB_OK;
+}
+
 // Returns 1 if launched, 0 if N is outside the range of this kernel.
 int mcosb_launch_sy2sb2(mcosb_ctx* ctx, int S, double* A, double* tau) {
     const int N = ctx->N;
     if (!sbr2_supported(ctx)) return 0;
+    const S2Config c = sbr2_config(N);
     const size_t smem = sbr2_smem(N);
     const int LD = sbr2_ld(N), LDZ = sbr2_ldz(N);
-    const int nw = sbr2_nw(N), qh = N <= 512 ? 1 : 2, rg = nw / 8;
     double *Zp, *Zc;
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S2_ZP, (size_t)S * 8 * qh * LDZ * 8, &Zp));
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S2_ZC, (size_t)S * rg * LDZ * 8, &Zc));
-#define S2_LAUNCH(NW, RPT, QH)                                                                                        \
-    do {                                                                                                              \
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(sy2sb2_kernel<NW, RPT, QH>,                                             \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-        sy2sb2_kernel<NW, RPT, QH><<<S, NW * 32, smem, ctx->stream>>>(A, N, LD, LDZ, tau, Zp, Zc);                    \
-    } while (0)
-    if (N <= 256) S2_LAUNCH(8, 1, 1);
-    else if (N <= 512) S2_LAUNCH(8, 2, 1);
-    else S2_LAUNCH(16, 2, 2);
-#undef S2_LAUNCH
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S2_ZP, (size_t)S * 8 * c.qh * LDZ * 8, &Zp));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S2_ZC, (size_t)S * (c.nw / 8) * LDZ * 8, &Zc));
+    if (c.nw == 8 && c.rpt == 1) MCOSB_TRY((s2_launch<8, 1, 1, 4, 2>(ctx, S, A, tau, smem, LD, LDZ, Zp, Zc)));
+    else if (c.nw == 8) MCOSB_TRY((s2_launch<8, 2, 1, 2, 2>(ctx, S, A, tau, smem, LD, LDZ, Zp, Zc)));
+    else if (c.rpt == 1 && c.sd == 6) MCOSB_TRY((s2_launch<16, 1, 1, 6, 1>(ctx, S, A, tau, smem, LD, LDZ, Zp, Zc)));
+    else if (c.rpt == 1) MCOSB_TRY((s2_launch<16, 1, 1, 4, 1>(ctx, S, A, tau, smem, LD, LDZ, Zp, Zc)));
+    else if (c.sd == 4) MCOSB_TRY((s2_launch<16, 2, 2, 4, 1>(ctx, S, A, tau, smem, LD, LDZ, Zp, Zc)));
+    else MCOSB_TRY((s2_launch<16, 2, 2, 0, 1>(ctx, S, A, tau, smem, LD, LDZ, Zp, Zc)));
     MCOSB_LAUNCHED(ctx, MK_SY2SB);
     return 1;
 }

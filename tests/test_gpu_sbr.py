@@ -165,24 +165,32 @@ def test_automatic_method_outside_the_two_stage_range():
         eng.set_eig_method(3)
 
 
-def test_round1_stage1_kernel_still_selectable():
-    """MCOSB_SY2SB_OLD=1 runs the round-1 dense -> band kernel (one 16-warp CTA per SM, N <= 696) for A/B timing."""
+@pytest.mark.parametrize("force_old", ["0", "1"])
+def test_both_stage1_kernels_over_their_size_ranges(force_old):
+    """The automatic choice uses the round-1 dense -> band kernel up to N = 696 and sy2sb2 above; MCOSB_SY2SB_OLD forces one
+    of them wherever it applies.  Both must give a band similar to the input over their whole range (two matrices per SM,
+    the cp.async ring with one and two column sub-passes, the register-ring variant above 640)."""
     import subprocess, sys, os, textwrap
-    code = textwrap.dedent("""
+    sizes = [10, 17, 64, 129, 255, 256, 257, 333, 440, 441, 500, 512, 513, 600, 640, 641, 696] + ([] if force_old == "1" else [777, 1000])
+    code = textwrap.dedent(f"""
         import numpy as np
         from mcos_b200.engine import Engine
-        n = 300
-        rng = np.random.RandomState(4)
-        a = np.stack([np.corrcoef(rng.standard_normal((2 * n, n)), rowvar=False) for _ in range(3)])
-        eng = Engine(n, 2 * n)
-        eng.set_eig_method(2)
-        d, e = eng.tridiagonalize(a)
-        for i in range(3):
-            t = np.diag(d[i]) + np.diag(e[i][:n - 1], 1) + np.diag(e[i][:n - 1], -1)
-            err = np.abs(np.linalg.eigvalsh(t) - np.linalg.eigvalsh(a[i])).max()
-            assert err < 1e-12 * n, err
+        for n in {sizes}:
+            rng = np.random.RandomState(n)
+            a = np.stack([np.corrcoef(rng.standard_normal((tt, n)), rowvar=False) for tt in (2 * n, max(2, n // 2))])
+            eng = Engine(n, 2 * n)
+            eng.set_eig_method(2)
+            d, e, work = eng.tridiagonalize(a, want_work=True)
+            for i in range(2):
+                ref = np.linalg.eigvalsh(a[i])
+                band = np.tril(work[i]) - np.tril(work[i], -9)
+                band = band + np.tril(band, -1).T
+                t = np.diag(d[i]) + np.diag(e[i][:n - 1], 1) + np.diag(e[i][:n - 1], -1)
+                assert np.abs(np.linalg.eigvalsh(band) - ref).max() < 2e-13 * n, (n, "band")
+                assert np.abs(np.linalg.eigvalsh(t) - ref).max() < 2e-13 * n, (n, "tridiagonal")
+            eng.close()
         print("ok")
     """)
-    env = dict(os.environ, MCOSB_SY2SB_OLD="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, MCOSB_SY2SB_OLD=force_old, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
