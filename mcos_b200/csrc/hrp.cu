@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
 #define GR_STAGE ((DM_BM + DM_BN / 2) * DM_LD_MMAJOR)   // doubles per pipeline stage: A (128 rows) + B (64 rows)
 template <bool VEC>
 __global__ void __launch_bounds__(GR_THREADS, 2)
-hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnall, int N, double* __restrict__ E2all) {
+hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnall, int N, double* __restrict__ E2all,
+                int take_sqrt) {
     // two CTAs of 4 warps per 128 x 128 tile, as in syrk_kernel: the column halves of an off-diagonal tile, the two warp
     // sets of the sub-block dealing on a diagonal one
     extern __shared__ double sm[];
@@ -227,6 +228,7 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
                 if (row < N && col < N && col <= row && (!diag || mb < 4 || two)) {
                     double v = fma(-2.0, acc[mb][nb][e], nr + rn[col]);
                     v = (col == row || v < 0.0) ? 0.0 : v;     // NaN passes through and sends the simulation to the fallback
+                    if (take_sqrt) v = sqrt(v);                 // NCO: distances, not squares (mcosb_launch_gram_dist)
                     E2[(size_t)row * N + col] = v;
                     E2[(size_t)col * N + row] = v;
                 }
@@ -706,6 +708,23 @@ __global__ void __launch_bounds__(BS_THREADS) hrp_bisect_kernel(const double* __
 }
 
 // Euclidean distances between the rows of D for S matrices (also used by NCO's silhouettes); the caller accounts for it.
+// Euclidean distances between the rows of D through the Gram matrix on the FP64 tensor cores: E_ij = sqrt(max(0, n_i + n_j -
+// 2 D_i . D_j)), rn = squared row norms.  What scikit-learn's euclidean_distances computes (same identity, same clipping at
+// zero) -- used by NCO's k-means++ / silhouettes, where scipy's sequential pdist arithmetic is not the reference.
+int mcosb_launch_gram_dist(mcosb_ctx* ctx, int S, const double* D, const double* rn, double* E) {
+    const int N = ctx->N;
+    const int ng = (N + DM_BM - 1) / DM_BM;
+    const size_t smem_g = (size_t)DM_STAGES * GR_STAGE * sizeof(double);
+    if (N % 2 == 0 && (uintptr_t)D % 16 == 0) {
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        hrp_gram_kernel<true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 1);
+    } else {
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        hrp_gram_kernel<false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 1);
+    }
+    return MCOSB_OK;
+}
+
 void mcosb_launch_euclid(mcosb_ctx* ctx, int S, const double* D, double* E) {
     const int nt = (ctx->N + EU_T - 1) / EU_T;
     hrp_euclid_kernel<<<dim3(nt * (nt + 1) / 2, S), 256, 0, ctx->stream>>>(D, ctx->N, E, nullptr);
@@ -738,10 +757,10 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
         const size_t smem_g = (size_t)DM_STAGES * GR_STAGE * sizeof(double);
         if (N % 2 == 0 && (uintptr_t)D % 16 == 0) {
             MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            hrp_gram_kernel<true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
+            hrp_gram_kernel<true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 0);
         } else {
             MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            hrp_gram_kernel<false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
+            hrp_gram_kernel<false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 0);
         }
         MCOSB_LAUNCHED(ctx, MK_HRP_GRAM);
         const int force = ctx->hrp_mode == 2 ? 1 : 0;

@@ -14,6 +14,7 @@
 // PARITY: the allocation algebra is pinned by the reference's goldens given a partition (tests/test_optimizer.py:30-47);
 // the clustering follows scikit-learn 1.9's algorithm, not bit for bit (sklearn computes distances through a GEMM
 // identity); agreement with sklearn's labels is measured in tests/test_gpu_nco.py.  "parity unpinned" vs sklearn 0.22.1.
+#include <cstdlib>
 #include <random>
 
 #include "common.cuh"
@@ -22,8 +23,10 @@
 #define NC_THREADS_MAX 512   // nco_cluster_kernel runs with 512 threads from N = 512 (one CTA per SM there anyway)
 #define NCT ((int)blockDim.x)
 #define NC_MAX_ITER 300
+#define NC_MP 4            // (cluster, coordinate) pairs a thread sums at once in the M-step
 
-__global__ void __launch_bounds__(256) nco_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D) {
+__global__ void __launch_bounds__(256) nco_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D,
+                                                       double* __restrict__ rn) {
     extern __shared__ double sg[];   // [N] square roots of the diagonal, once per CTA (32 rows)
     const int s = blockIdx.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -35,17 +38,23 @@ __global__ void __launch_bounds__(256) nco_dist_kernel(const double* __restrict_
         const int row = blockIdx.x * 32 + wid * 4 + q;
         if (row >= N) return;
         const double si = sg[row];
+        double nrm = 0.0;
         for (int j = lane; j < N; j += 32) {
             double r = __ddiv_rn(c[(size_t)row * N + j], __dmul_rn(si, sg[j]));
             r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
             if (r != r) r = 0.0;  // corr.fillna(0)
-            d[(size_t)row * N + j] = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
+            const double v = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
+            d[(size_t)row * N + j] = v;
+            nrm = fma(v, v, nrm);
         }
+        nrm = warp_sum(nrm);           // squared row norm for the Gram form of the row distances
+        if (lane == 0) rn[(size_t)s * N + row] = nrm;
     }
 }
 
 // declared in hrp.cu
 void mcosb_launch_euclid(mcosb_ctx* ctx, int S, const double* D, double* E);
+int mcosb_launch_gram_dist(mcosb_ctx* ctx, int S, const double* D, const double* rn, double* E);
 
 struct NcSm {
     double* centers;   // [kmax][N]
@@ -153,6 +162,11 @@ __device__ void nc_block_sum_multi(double (&v)[NC_CG], NcSm& s) {
 }
 
 // E-step: labels[i] = argmin_j (||c_j||^2 - 2 x_i.c_j), lowest j on ties.
+// One thread per point and chunk of NC_JC centres: the point's column of X is read once per chunk and feeds NC_JC x 4
+// accumulator chains (the (point, centre)-pair version re-read the column for every centre with 4 loads in flight per
+// thread: 100 of 138 M cycles per simulation at N = 1000, all of it L2 latency).  Per pair the arithmetic is unchanged --
+// four chains over d mod 4, (a0 + a1) + (a2 + a3), strict < over ascending j -- so the labels are bit for bit the old ones.
+#define NC_JC 8
 __device__ void nc_assign(const double* __restrict__ X, int N, int k, NcSm& s) {
     for (int j = threadIdx.x; j < k; j += NCT) {
         double q = 0.0;
@@ -160,30 +174,41 @@ __device__ void nc_assign(const double* __restrict__ X, int N, int k, NcSm& s) {
         s.cn2[j] = q;
     }
     __syncthreads();
-    // one thread per (point, centre) pair (only N of the CTA's threads would work with one thread per point); the scores
-    // go through s.cnew (free during the E-step), then each point takes the argmin, lowest j on ties
-    double* score = s.cnew;
-    for (int p = threadIdx.x; p < N * k; p += NCT) {
-        const int i = p % N, j = p / N;
-        const double* ca = s.centers + j * N;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int d = 0;
-        for (; d + 3 < N; d += 4) {
-            a0 = fma(X[(size_t)d * N + i] - s.colmean[d], ca[d], a0);
-            a1 = fma(X[(size_t)(d + 1) * N + i] - s.colmean[d + 1], ca[d + 1], a1);
-            a2 = fma(X[(size_t)(d + 2) * N + i] - s.colmean[d + 2], ca[d + 2], a2);
-            a3 = fma(X[(size_t)(d + 3) * N + i] - s.colmean[d + 3], ca[d + 3], a3);
-        }
-        for (; d < N; ++d) a0 = fma(X[(size_t)d * N + i] - s.colmean[d], ca[d], a0);
-        score[p] = s.cn2[j] - 2.0 * ((a0 + a1) + (a2 + a3));
-    }
-    __syncthreads();
     for (int i = threadIdx.x; i < N; i += NCT) {
         double bestv = INFINITY;
         int bestj = 0;
-        for (int j = 0; j < k; ++j) {
-            const double v = score[j * N + i];
-            if (v < bestv) { bestv = v; bestj = j; }
+        for (int j0 = 0; j0 < k; j0 += NC_JC) {
+            const int nj = min(NC_JC, k - j0);
+            const double* ca = s.centers + (size_t)j0 * N;
+            double a[NC_JC][4];
+#pragma unroll
+            for (int jj = 0; jj < NC_JC; ++jj) a[jj][0] = a[jj][1] = a[jj][2] = a[jj][3] = 0.0;
+            int d = 0;
+            for (; d + 3 < N; d += 4) {
+                double x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = X[(size_t)(d + e) * N + i] - s.colmean[d + e];
+#pragma unroll
+                for (int jj = 0; jj < NC_JC; ++jj) {
+                    if (jj < nj) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) a[jj][e] = fma(x[e], ca[(size_t)jj * N + d + e], a[jj][e]);
+                    }
+                }
+            }
+            for (; d < N; ++d) {
+                const double x0 = X[(size_t)d * N + i] - s.colmean[d];
+#pragma unroll
+                for (int jj = 0; jj < NC_JC; ++jj)
+                    if (jj < nj) a[jj][0] = fma(x0, ca[(size_t)jj * N + d], a[jj][0]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < NC_JC; ++jj) {
+                if (jj < nj) {
+                    const double v = s.cn2[j0 + jj] - 2.0 * ((a[jj][0] + a[jj][1]) + (a[jj][2] + a[jj][3]));
+                    if (v < bestv) { bestv = v; bestj = j0 + jj; }
+                }
+            }
         }
         s.labels[i] = bestj;
     }
@@ -319,20 +344,44 @@ __global__ void __launch_bounds__(NC_THREADS_MAX) nco_cluster_kernel(const doubl
                     if (s.labels[i] == j) s.members[pos++] = i;
             }
             __syncthreads();
-            for (int idx = tid; idx < k * N; idx += NCT) {
-                const int j = idx / N, d = idx % N;
-                const double cmd = s.colmean[d];
-                const int e1 = s.cstart[j + 1];
-                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-                int e = s.cstart[j];
-                for (; e + 3 < e1; e += 4) {
-                    c0 += X[(size_t)s.members[e] * N + d] - cmd;
-                    c1 += X[(size_t)s.members[e + 1] * N + d] - cmd;
-                    c2 += X[(size_t)s.members[e + 2] * N + d] - cmd;
-                    c3 += X[(size_t)s.members[e + 3] * N + d] - cmd;
+            // new centres: every (cluster, coordinate) pair is a sum over the cluster's members in four chains (e mod 4);
+            // a thread runs NC_MP pairs at once so that 4 NC_MP loads are in flight instead of 4
+            for (int idx0 = tid; idx0 < k * N; idx0 += NC_MP * NCT) {
+                double c[NC_MP][4];
+                int e[NC_MP], e1[NC_MP], dd[NC_MP];
+                double cmd[NC_MP];
+                bool live[NC_MP];
+#pragma unroll
+                for (int u = 0; u < NC_MP; ++u) {
+                    const int idx = idx0 + u * NCT;
+                    live[u] = idx < k * N;
+                    const int j = live[u] ? idx / N : 0;
+                    dd[u] = live[u] ? idx % N : 0;
+                    cmd[u] = s.colmean[dd[u]];
+                    e[u] = live[u] ? s.cstart[j] : 0;
+                    e1[u] = live[u] ? s.cstart[j + 1] : 0;
+                    c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.0;
                 }
-                for (; e < e1; ++e) c0 += X[(size_t)s.members[e] * N + d] - cmd;
-                s.cnew[idx] = (c0 + c1) + (c2 + c3);
+                bool more = true;
+                while (more) {
+                    more = false;
+#pragma unroll
+                    for (int u = 0; u < NC_MP; ++u) {
+                        if (e[u] + 3 < e1[u]) {
+                            c[u][0] += X[(size_t)s.members[e[u]] * N + dd[u]] - cmd[u];
+                            c[u][1] += X[(size_t)s.members[e[u] + 1] * N + dd[u]] - cmd[u];
+                            c[u][2] += X[(size_t)s.members[e[u] + 2] * N + dd[u]] - cmd[u];
+                            c[u][3] += X[(size_t)s.members[e[u] + 3] * N + dd[u]] - cmd[u];
+                            e[u] += 4;
+                            more |= e[u] + 3 < e1[u];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NC_MP; ++u) {
+                    for (; e[u] < e1[u]; ++e[u]) c[u][0] += X[(size_t)s.members[e[u]] * N + dd[u]] - cmd[u];
+                    if (live[u]) s.cnew[idx0 + u * NCT] = (c[u][0] + c[u][1]) + (c[u][2] + c[u][3]);
+                }
             }
             __syncthreads();
             if (tid == 0) {
@@ -404,11 +453,18 @@ __global__ void __launch_bounds__(NC_THREADS_MAX) nco_cluster_kernel(const doubl
         for (int i = tid; i < N; i += NCT) atomicAdd(&s.counts[s.labels[i]], 1);
         for (int idx = tid; idx < k * N; idx += NCT) dsum[idx] = 0.0;
         __syncthreads();
-        for (int i = tid; i < N; i += NCT) {
-            for (int jx = 0; jx < N; ++jx) {
-                if (jx == i) continue;
-                dsum[s.labels[jx] * N + i] += E[(size_t)jx * N + i];
+        for (int i = tid; i < N; i += NCT) {       // adds in ascending jx as before; the loads run 8 ahead of them
+            int jx = 0;
+            for (; jx + 7 < N; jx += 8) {
+                double ev[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ev[u] = E[(size_t)(jx + u) * N + i];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (jx + u != i) dsum[s.labels[jx + u] * N + i] += ev[u];
             }
+            for (; jx < N; ++jx)
+                if (jx != i) dsum[s.labels[jx] * N + i] += E[(size_t)jx * N + i];
         }
         __syncthreads();
         double ssum = 0.0;
@@ -469,17 +525,22 @@ __device__ bool nc_chol_solve(double* __restrict__ A, int n, int lda, double* __
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < n; ++i) {
-            double t = b[i];
-            for (int j = 0; j < i; ++j) t -= A[(size_t)i * lda + j] * b[j];
-            b[i] = t / A[(size_t)i * lda + i];
-        }
-        for (int i = n - 1; i >= 0; --i) {
-            double t = b[i];
-            for (int j = i + 1; j < n; ++j) t -= A[(size_t)j * lda + i] * b[j];
-            b[i] = t / A[(size_t)i * lda + i];
-        }
+    // triangular solves, column-oriented and block-parallel (one thread did both, 2 n^2 / 2 dependent global loads: 30 of
+    // 31 M cycles per simulation at N = 1000 with ten 100 x 100 clusters).  Forward: row i still subtracts its products in the
+    // order k = 0 .. i - 1 with one FMA each, as the serial loop did; backward: in the order k = n - 1 .. i + 1.
+    for (int k = 0; k < n; ++k) {            // L t = b
+        __syncthreads();
+        const double xk = b[k] / A[(size_t)k * lda + k];
+        __syncthreads();
+        if (threadIdx.x == 0) b[k] = xk;
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) b[i] = fma(-A[(size_t)i * lda + k], xk, b[i]);
+    }
+    for (int k = n - 1; k >= 0; --k) {       // L' x = t
+        __syncthreads();
+        const double xk = b[k] / A[(size_t)k * lda + k];
+        __syncthreads();
+        if (threadIdx.x == 0) b[k] = xk;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) b[i] = fma(-A[(size_t)k * lda + i], xk, b[i]);
     }
     __syncthreads();
     return ok;
@@ -613,10 +674,22 @@ int mcosb_dev_nco(mcosb_ctx* ctx, int S, const double* dmu, const double* dcov, 
         double *D, *E;
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_WORK, (size_t)S * n * n, &D));
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_E, (size_t)S * n * n, &E));
-        nco_dist_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, D);
+        double* rn;
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_HRP_RN, (size_t)S * n, &rn));
+        nco_dist_kernel<<<dim3((N + 31) / 32, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, D, rn);
         MCOSB_LAUNCHED(ctx, MK_NCO_DIST);
-        mcosb_launch_euclid(ctx, S, D, E);
-        MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
+        // Euclidean distances between the rows of D (k-means++ potentials, silhouettes).  scikit-learn forms them through
+        // the Gram identity with clipping at zero; so does this (FP64 tensor cores: 33 instead of 103 us per simulation at
+        // N = 1000 for scipy's sequential pdist arithmetic, which is HRP's reference, not NCO's).  MCOSB_NCO_EXACT_DIST=1
+        // keeps the exact kernel (A/B of the partitions).
+        static const bool exact_dist = getenv("MCOSB_NCO_EXACT_DIST") != nullptr;
+        if (exact_dist) {
+            mcosb_launch_euclid(ctx, S, D, E);
+            MCOSB_LAUNCHED(ctx, MK_HRP_EUCLID);
+        } else {
+            MCOSB_TRY(mcosb_launch_gram_dist(ctx, S, D, rn, E));
+            MCOSB_LAUNCHED(ctx, MK_HRP_GRAM);
+        }
         const int ntr_max = 2 + (int)std::log((double)max_k);
         const int ustride = 1 + (max_k - 1) * ntr_max;
         std::vector<double> tab;

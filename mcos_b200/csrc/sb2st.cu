@@ -403,11 +403,15 @@ int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double
     const int N = ctx->N;
     const size_t smem = (size_t)(N + 16) * 16 * sizeof(double);
     if (smem + 1024 > (size_t)ctx->smem_optin || N > 1024) return 0;
-    static int Wsel = -1;
-    if (Wsel < 0) {
+    static int Wenv = -1;
+    if (Wenv < 0) {
         const char* e = getenv("MCOSB_SB2ST_W");
-        Wsel = e ? atoi(e) : 5;   // measured at N = 500 (us per matrix): W = 3 8.50, 4 6.89, 5 6.60, 6 7.22, 8 7.26
+        Wenv = e ? atoi(e) : 0;
     }
+    // warps pipelining the sweeps of one matrix.  Three matrices share an SM up to N = 512 (64 KB of band each): measured at
+    // N = 500 (us per matrix): W = 3 8.50, 4 6.89, 5 6.60, 6 7.22, 8 7.26.  Above, the band takes the SM to two matrices and
+    // then (N > 880) to one, and a sweep has up to 125 steps to pipeline: more warps per matrix (profiles/sbr_r02.md).
+    const int Wsel = Wenv > 0 ? Wenv : (N <= 512 ? 5 : (N <= 880 ? 8 : 16));
 #define SB2ST_LAUNCH(W)                                                                                               \
     do {                                                                                                              \
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -434,6 +438,8 @@ int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double
     else if (Wsel == 4) SB2ST_LAUNCH(4);
     else if (Wsel == 6) SB2ST_LAUNCH(6);
     else if (Wsel == 8) SB2ST_LAUNCH(8);
+    else if (Wsel == 12) SB2ST_LAUNCH(12);
+    else if (Wsel == 16) SB2ST_LAUNCH(16);
     else SB2ST_LAUNCH(5);
 #undef SB2ST_LAUNCH
 #undef SB2ST_LAUNCH_MMA
