@@ -288,6 +288,7 @@ extern "C" int mcosb_set_profiling(mcosb_ctx* ctx, int on) {
     ctx->kev.clear();
     for (int i = 0; i < MK_COUNT; ++i) { ctx->kernel_ms[i] = 0.0; ctx->kernel_launches[i] = 0; }
     ctx->profile = on != 0;
+    MCOSB_PROFILE_MARK(ctx);   // anchor: the first kernel launched after this call has a predecessor to be timed against
     return MCOSB_OK;
 }
 
