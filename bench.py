@@ -330,8 +330,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")        # keep stdout to the one JSON line (NCCL prints its version there at these levels)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
