@@ -95,11 +95,16 @@ __global__ void __launch_bounds__(NW * 32, 1)
 sy2sb_kernel(double* Aall, int N, int LD, double* __restrict__ tauall) {
     constexpr int NT = NW * 32;
     extern __shared__ double sm[];
-    double* Vp = sm;                          // [8][LD]   k-major: element (row i, k) at [k * LD + i]
-    double* Wp = Vp + 8 * (size_t)LD;
-    double* Vn = Wp + 8 * (size_t)LD;
-    double* Zz = Vn + 8 * (size_t)LD;
-    double* part = Zz + 8 * (size_t)LD;       // [2][8 column classes][32 rows][8]
+    // four k-major panel arrays [8][LD] (element (row i, k) at [k * LD + i]) in two pairs that swap roles every panel:
+    // (V_p, W_p) = pair `flip`, (V_n, Z / W_n) = the other.  The addresses are derived from `flip` where they are used
+    // (four rotating pointer variables cost two spilled registers that every warp reloaded from L2 -- the L1 is 28 KB next
+    // to 182 KB of shared memory -- right before the barrier of every 32-row block row).
+    double* part = sm + 32 * (size_t)LD;      // [2][8 column classes][32 rows][8]
+    int flip = 0;
+#define Vp (sm + (flip ? 16 * LD : 0))
+#define Wp (sm + (flip ? 24 * LD : 8 * LD))
+#define Vn (sm + (flip ? 0 : 16 * LD))
+#define Zz (sm + (flip ? 8 * LD : 24 * LD))
     double* red = part + 2 * 8 * 32 * 8;      // [2][NW][8]
     double* rowc = red + 2 * NW * 8;          // [2][8]
     double* Gm = rowc + 16;                   // [8][8] strictly upper part of V'V (T^-1 = striu(V'V) + diag(1/tau))
@@ -545,8 +550,7 @@ sy2sb_kernel(double* Aall, int N, int LD, double* __restrict__ tauall) {
         __syncthreads();
         S1_TICK(4);
         // rotate: (Vp, Wp) <- (Vn, Wn)
-        double* tp = Vp; Vp = Vn; Vn = tp;
-        tp = Wp; Wp = Zz; Zz = tp;
+        flip ^= 1;
         first = false;
     }
 #ifdef S1_TIMING
@@ -555,6 +559,11 @@ sy2sb_kernel(double* Aall, int N, int LD, double* __restrict__ tauall) {
                s1_acc[2], s1_acc[3], s1_acc[4]);
 #endif
 }
+
+#undef Vp
+#undef Wp
+#undef Vn
+#undef Zz
 
 // LD = 8 (mod 16) keeps the 8-lane x 4-k fragment loads of the k-major arrays on distinct banks; >= N + 32 so block
 // rows may overhang N (those rows hold zeros).

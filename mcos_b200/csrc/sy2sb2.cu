@@ -106,10 +106,13 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
     constexpr int RG = NW / 8;
     constexpr int NCLS = 8 * QH;
     extern __shared__ double sm[];
-    double* Vp = sm;                          // [8][LD]   k-major: element (row i, k) at [k * LD + i]
-    double* Wp = Vp + 8 * (size_t)LD;
-    double* Vn = Wp + 8 * (size_t)LD;
-    double* red = Vn + 8 * (size_t)LD;        // [2][NW][8]
+    // three k-major panel arrays [8][LD] (element (row i, k) at [k * LD + i]): W_p in the middle, V_p and V_n swap ends every
+    // panel; their addresses are derived from `flip` at the point of use (rotating pointer variables cost spilled registers)
+    int flip = 0;
+#define Vp (sm + (flip ? 16 * LD : 0))
+#define Wp (sm + 8 * LD)
+#define Vn (sm + (flip ? 0 : 16 * LD))
+    double* red = sm + 24 * (size_t)LD;       // [2][NW][8]
     double* rowc = red + 2 * NW * 8;          // [2][8]
     double* Gm = rowc + 16;                   // [8][8] strictly upper part of V'V (T^-1 = striu(V'V) + diag(1/tau))
     double* tauS = Gm + 64;                   // [8]
@@ -625,7 +628,7 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
         __syncthreads();
         S2_TICK(4);
         // rotate: V_p <- V_n, W_p stays where W_n was just written, the old V_p array becomes the next V_n
-        double* tp = Vp; Vp = Vn; Vn = tp;
+        flip ^= 1;
     }
 #ifdef S2_TIMING
     if (tid == 0 && blockIdx.x == 0)
@@ -633,6 +636,10 @@ sy2sb2_kernel(double* Aall, int N, int LD, int LDZ, double* __restrict__ tauall,
                s2_acc[2], s2_acc[3], s2_acc[4]);
 #endif
 }
+
+#undef Vp
+#undef Wp
+#undef Vn
 
 // LD = 8 (mod 16) keeps the 16-byte fragment loads of the k-major arrays on distinct bank groups (MCOSB_S2_LDMOD for
 // experiments); >= N + 16 so the last 16-row block row may overhang N (those rows hold zeros).

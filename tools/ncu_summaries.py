@@ -37,7 +37,7 @@ def launches(csv_path, bench_path):
     total = sum(v[1] for v in tot.values())
     print("| kernel | launches | total ms | share (ncu) | share (bench events) |\n|---|---|---|---|---|")
     for n, (c, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        key = n.replace("void ", "").split("<")[0]
+        key = n.replace("void ", "").split("<")[0].replace("trmm2_kernel", "trmm_kernel")
         print(f"| {n[:60]} | {c} | {ms:.3f} | {ms / total:.4f} | {bench.get(key, '')} |")
 
 
