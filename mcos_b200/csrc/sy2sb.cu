@@ -28,6 +28,9 @@
 
 
 #define S1_D 2    // tiles in flight per warp (register ring), a power of two
+#ifndef S1_L2_PREFETCH
+#define S1_L2_PREFETCH 0   // block rows ahead of an L2 prefetch of the tiles; measured 0: 18.36, 1: 18.37, 4: 19.09 us -- off
+#endif
 
 #ifdef S1_TIMING
 #define S1_TICK(idx) do { if (threadIdx.x == 0) { long long now__ = clock64(); s1_acc[idx] += now__ - s1_last; s1_last = now__; } } while (0)
@@ -320,6 +323,24 @@ sy2sb_kernel(double* Aall, int N, int LD, double* __restrict__ tauall) {
             const int par = n & 1;
             double* rowbase = A + (size_t)(i0 + g) * N + 8 * wc + 2 * t;
             const double* nextbase = rowbase + (size_t)32 * N;
+#if S1_L2_PREFETCH
+            // pull this warp's tiles of block row n + S1_L2_PREFETCH towards L2 (no registers, no scoreboard): 28 % of the tile
+            // loads miss L2 (one matrix per SM = 150 MB of triangles against 126 MB), and the register ring only covers an L2
+            // hit.  One instruction per tile: lanes 0-15 touch the first byte of the tile's 16 row segments (64 B each),
+            // lanes 16-31 the last, so segments that straddle a line are covered.
+            {
+                const int np = n + S1_L2_PREFETCH;
+                if (np < nbr) {
+                    const int prow = R0 + 32 * np + 16 * wh + (lane & 15);
+                    if (prow < N) {
+                        const double* pbase = A + (size_t)prow * N + 8 * wc + ((lane & 16) ? 7 : 0);
+                        const int qh = qhi_of(np);
+                        for (int q = qlo; q <= qh; ++q)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(pbase + 64 * q));
+                    }
+                }
+            }
+#endif
             // slots this block row does not use take their tile of the next block row now
 #pragma unroll
             for (int d = 0; d < S1_D; ++d) {
