@@ -142,10 +142,9 @@ __global__ void __launch_bounds__(256) hrp_euclid_kernel(const double* __restric
 // ---------------------------------------------------------------------------------------------------------------
 #define GR_THREADS 128
 #define GR_STAGE ((DM_BM + DM_BN / 2) * DM_LD_MMAJOR)   // doubles per pipeline stage: A (128 rows) + B (64 rows)
-template <bool VEC>
+template <bool VEC, bool TAKE_SQRT>
 __global__ void __launch_bounds__(GR_THREADS, 2)
-hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnall, int N, double* __restrict__ E2all,
-                int take_sqrt) {
+hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnall, int N, double* __restrict__ E2all) {
     // two CTAs of 4 warps per 128 x 128 tile, as in syrk_kernel: the column halves of an off-diagonal tile, the two warp
     // sets of the sub-block dealing on a diagonal one
     extern __shared__ double sm[];
@@ -228,7 +227,7 @@ hrp_gram_kernel(const double* __restrict__ Dall, const double* __restrict__ rnal
                 if (row < N && col < N && col <= row && (!diag || mb < 4 || two)) {
                     double v = fma(-2.0, acc[mb][nb][e], nr + rn[col]);
                     v = (col == row || v < 0.0) ? 0.0 : v;     // NaN passes through and sends the simulation to the fallback
-                    if (take_sqrt) v = sqrt(v);                 // NCO: distances, not squares (mcosb_launch_gram_dist)
+                    if (TAKE_SQRT) v = sqrt(v);                 // NCO: distances, not squares (mcosb_launch_gram_dist)
                     E2[(size_t)row * N + col] = v;
                     E2[(size_t)col * N + row] = v;
                 }
@@ -716,11 +715,11 @@ int mcosb_launch_gram_dist(mcosb_ctx* ctx, int S, const double* D, const double*
     const int ng = (N + DM_BM - 1) / DM_BM;
     const size_t smem_g = (size_t)DM_STAGES * GR_STAGE * sizeof(double);
     if (N % 2 == 0 && (uintptr_t)D % 16 == 0) {
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-        hrp_gram_kernel<true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 1);
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        hrp_gram_kernel<true, true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
     } else {
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-        hrp_gram_kernel<false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 1);
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        hrp_gram_kernel<false, true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
     }
     return MCOSB_OK;
 }
@@ -756,11 +755,11 @@ int mcosb_dev_hrp(mcosb_ctx* ctx, int S, const double* dcov, double* dw, int* do
         const int ng = (N + DM_BM - 1) / DM_BM;
         const size_t smem_g = (size_t)DM_STAGES * GR_STAGE * sizeof(double);
         if (N % 2 == 0 && (uintptr_t)D % 16 == 0) {
-            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            hrp_gram_kernel<true><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 0);
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            hrp_gram_kernel<true, false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
         } else {
-            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-            hrp_gram_kernel<false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E, 0);
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(hrp_gram_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+            hrp_gram_kernel<false, false><<<dim3(ng * (ng + 1), S), GR_THREADS, smem_g, ctx->stream>>>(D, rn, N, E);
         }
         MCOSB_LAUNCHED(ctx, MK_HRP_GRAM);
         const int force = ctx->hrp_mode == 2 ? 1 : 0;
