@@ -90,6 +90,14 @@ int mcosb_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* X);
  * (0 for the other kinds). */
 int mcosb_moments(mcosb_ctx* ctx, int S, const double* X, int kind, double* mu_hat, double* cov_hat, double* shrink);
 
+/* simulate() for simulations sim_id0 .. sim_id0 + S - 1 in one call (observation_simulator.py:26-28 / 38-40 / 50-57): the
+ * draws never leave the device, and -- as inside mcosb_run -- they are kept centred by the TRUE mean (Y = X - mu), so the
+ * sample mean is mu + mean(Y) and the covariance (Y'Y - T ybar ybar') / (T - 1) needs no centring pass.  Composing this
+ * call with the stage entry points below reproduces mcosb_run bit for bit; mcosb_sample + mcosb_moments agree with it to
+ * rounding (1e-13).  shrink[S] nullable. */
+int mcosb_sample_moments(mcosb_ctx* ctx, uint64_t sim_id0, int S, int kind, double* mu_hat, double* cov_hat,
+                         double* shrink);
+
 /* DeNoiserCovarianceTransformer.transform (covariance_transformer.py:62-97), in place on cov[S][N][N].
  * Nullable outputs: eigvals[S][N] (descending), var[S] (fitted MP variance), n_facts[S], status[S]. */
 int mcosb_denoise(mcosb_ctx* ctx, int S, double* cov_inout, int n_obs, double bandwidth, double* eigvals, double* var,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mcosb_set_truth": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mcosb_sample": (c_int, [c_void_p, c_uint64, c_int, c_void_p]),
     "mcosb_moments": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "mcosb_sample_moments": (c_int, [c_void_p, c_uint64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mcosb_denoise": (c_int, [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcosb_set_eig_method": (c_int, [c_void_p, c_int]),
     "mcosb_tridiagonalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -302,11 +302,15 @@ __device__ __forceinline__ double lw_shrink(double c, double sh, double m, bool 
 // ---------------------------------------------------------------------------------------------------------------
 // internal (device-pointer) stage entry points used by the public wrappers and by mcosb_run
 // ---------------------------------------------------------------------------------------------------------------
-int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX);
+// add_mu = false: dX receives Y = Z L' = X - mu (the draws centred by the TRUE mean), for mcosb_dev_moments(..., shift = true mu)
+int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool add_mu = true);
 // lwcoef_defer (Ledoit-Wolf only): instead of shrinking dcov in place, leave S_b there and write (shrinkage, mean
 // variance) per simulation to lwcoef_defer[2 s .. 2 s + 1]; mcosb_dev_denoise applies them while it forms the correlation
+// shift (device, [N]) != nullptr: dX holds the draws MINUS this vector (mcosb_dev_sample with add_mu = false); the means get
+// it added back, and the covariance is formed as (Y'Y - T ybar ybar') / (T - 1) without centring in the GEMM loop -- exact
+// algebra, and well conditioned because ybar is O(sigma / sqrt(T)).
 int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink,
-                      double* lwcoef_defer = nullptr);
+                      double* lwcoef_defer = nullptr, const double* shift = nullptr);
 int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
                       int* dnf, int* dstatus, const double* lwcoef = nullptr);
 // *q2 receives the stage-2 reflectors when the two-stage tridiagonalisation was used (then A holds the panel reflectors

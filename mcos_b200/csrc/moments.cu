@@ -13,8 +13,11 @@
 #define CM_COLS 32
 #define CM_ROWGROUPS 8
 
+// shift != nullptr: X holds draws minus `shift`; ybar (the mean of what is stored) goes to `mean`, shift + ybar to `mean_out`
 __global__ void __launch_bounds__(CM_COLS* CM_ROWGROUPS) colmean_kernel(const double* __restrict__ X, int T, int N,
-                                                                        double* __restrict__ mean) {
+                                                                        double* __restrict__ mean,
+                                                                        const double* __restrict__ shift,
+                                                                        double* __restrict__ mean_out) {
     __shared__ double part[CM_ROWGROUPS][CM_COLS];
     const int s = blockIdx.y;
     const int col = blockIdx.x * CM_COLS + (threadIdx.x % CM_COLS);
@@ -29,7 +32,9 @@ __global__ void __launch_bounds__(CM_COLS* CM_ROWGROUPS) colmean_kernel(const do
         double tot = 0.0;
 #pragma unroll
         for (int r = 0; r < CM_ROWGROUPS; ++r) tot += part[r][threadIdx.x];
-        mean[(size_t)s * N + col] = tot / (double)T;
+        const double m = tot / (double)T;
+        mean[(size_t)s * N + col] = m;
+        if (shift) mean_out[(size_t)s * N + col] = shift[col] + m;
     }
 }
 
@@ -48,8 +53,11 @@ __device__ __forceinline__ void tile_ij(int p, int& I, int& J) {
 // 2 x 16 + 2 x 20 DMMA per k-step).  lwpart[s][cta][2] receives (sum of squares of the scaled entries this CTA stands
 // for in the full symmetric matrix, trace contribution).
 // VEC: 16-byte cp.async (N even and X 16-byte aligned), otherwise 8-byte copies.
+// CENTER = false: the data are already (nearly) centred -- the fused loop hands over Y = X - true mu -- and the products are
+// taken raw, cov = (Y'Y - T ybar ybar') scale in the epilogue: the per-fragment subtractions of the centred form are DADDs on
+// the pipe the DMMAs run on, 20 % of the kernel in the ncu source view (profiles/kernels_r02.md).
 #define SY_THREADS 128
-template <bool VEC>
+template <bool VEC, bool CENTER>
 __global__ void __launch_bounds__(SY_THREADS, 2)
 syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T, int N, double scale,
             double* __restrict__ cov, double* __restrict__ lwpart) {
@@ -155,8 +163,8 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
             if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
             cp_async_commit();
         };
-        if (diag) dmma_slab_diag<true, true>(At, dwid, lane, acc, next, amean, bmean, T - kt * DM_BK);
-        else dmma_slab<true, true, true>(At, Bt, wm0, wn0, lane, acc, next, amean, bmean, T - kt * DM_BK);
+        if (diag) dmma_slab_diag<true, CENTER>(At, dwid, lane, acc, next, amean, bmean, T - kt * DM_BK);
+        else dmma_slab<true, true, CENTER>(At, Bt, wm0, wn0, lane, acc, next, amean, bmean, T - kt * DM_BK);
     }
 
 #ifdef SYRK_TIMING
@@ -177,7 +185,8 @@ syrk_kernel(const double* __restrict__ X, const double* __restrict__ mean, int T
                 int row = I * DM_BM + (diag ? (mb < 4 ? r0a + mb * 8 : r0b + (mb - 4) * 8) : wm0 + mb * 8) + g;
                 int col = (diag ? J * DM_BN + (mb < 4 ? c0a : c0b) : jcol0 + wn0) + nb * 8 + 2 * t4 + e;
                 if (row < N && col < N && col <= row && (!diag || mb < 4 || two)) {
-                    double v = acc[mb][nb][e] * scale;
+                    double v = CENTER ? acc[mb][nb][e] * scale
+                                      : fma(-(double)T * mu[row], mu[col], acc[mb][nb][e]) * scale;
                     c[(size_t)row * N + col] = v;
                     if (col != row) {
                         c[(size_t)col * N + row] = v;
@@ -292,7 +301,7 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
 }
 
 int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink,
-                      double* lwcoef_defer) {
+                      double* lwcoef_defer, const double* shift) {
     if (kind < 0 || kind > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown moments kind");
     if (S == 0) return MCOSB_OK;
     const int N = ctx->N, T = ctx->T;
@@ -301,8 +310,11 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
     if (kind == MCOSB_MOMENTS_MUCOV && T < 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "covariance needs T >= 2");
     const bool lw = (kind == MCOSB_MOMENTS_LEDOIT_WOLF);
 
+    // with a shift the statistics are taken of Y = X - shift: ybar in scratch, shift + ybar reported as the mean
+    double* dmean = dmu;
+    if (shift) MCOSB_TRY(mcosb_scratch_t(ctx, SL_COLMEAN, (size_t)S * N, &dmean));
     dim3 gm((N + CM_COLS - 1) / CM_COLS, S);
-    colmean_kernel<<<gm, CM_COLS * CM_ROWGROUPS, 0, ctx->stream>>>(dX, T, N, dmu);
+    colmean_kernel<<<gm, CM_COLS * CM_ROWGROUPS, 0, ctx->stream>>>(dX, T, N, dmean, shift, dmu);
     MCOSB_LAUNCHED(ctx, MK_COLMEAN);
 
     const int nt = (N + DM_BM - 1) / DM_BM, ntiles = 2 * (nt * (nt + 1) / 2);   // two CTAs per 128 x 128 tile
@@ -310,20 +322,24 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
     if (lw) MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWPART, (size_t)S * ntiles * 2, &lwpart));
     const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_KMAJOR * sizeof(double);
     const double scale = lw ? 1.0 / T : 1.0 / (T - 1);
-    if (N % 2 == 0 && (uintptr_t)dX % 16 == 0) {
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        syrk_kernel<true><<<dim3(ntiles, S), SY_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
-    } else {
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        syrk_kernel<false><<<dim3(ntiles, S), SY_THREADS, smem, ctx->stream>>>(dX, dmu, T, N, scale, dcov, lwpart);
-    }
+    const bool vec = N % 2 == 0 && (uintptr_t)dX % 16 == 0;
+#define SY_LAUNCH(V, C)                                                                                               \
+    do {                                                                                                              \
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel<V, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        syrk_kernel<V, C><<<dim3(ntiles, S), SY_THREADS, smem, ctx->stream>>>(dX, dmean, T, N, scale, dcov, lwpart);    \
+    } while (0)
+    if (vec && !shift) SY_LAUNCH(true, true);
+    else if (vec) SY_LAUNCH(true, false);
+    else if (!shift) SY_LAUNCH(false, true);
+    else SY_LAUNCH(false, false);
+#undef SY_LAUNCH
     MCOSB_LAUNCHED(ctx, MK_SYRK);
 
     if (lw) {
         const int nchunks = (T + RN_ROWS - 1) / RN_ROWS;
         double* rnpart = nullptr;
         MCOSB_TRY(mcosb_scratch_t(ctx, SL_LWSTAT, (size_t)S * nchunks, &rnpart));
-        lw_rownorm_kernel<<<dim3(nchunks, S), 256, 0, ctx->stream>>>(dX, dmu, T, N, rnpart);
+        lw_rownorm_kernel<<<dim3(nchunks, S), 256, 0, ctx->stream>>>(dX, dmean, T, N, rnpart);
         MCOSB_LAUNCHED(ctx, MK_LW_ROWNORM);
         if (lwcoef_defer) {
             lw_coef_kernel<<<(S + 127) / 128, 128, 0, ctx->stream>>>(lwpart, ntiles, rnpart, nchunks, T, N, S, lwcoef_defer);

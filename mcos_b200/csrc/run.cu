@@ -75,11 +75,13 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, const RunPlan& rp, ui
     for (int c0 = 0; c0 < W; c0 += CH) {
         const int nc = std::min(CH, W - c0);
         MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, true));
-        MCOSB_TRY(mcosb_dev_sample(ctx, sim0 + c0, nc, dX));
+        // the draws stay centred by the TRUE mean (Y = Z L'): the moment kernels add it back to the sample mean and take the
+        // covariance of Y without centring inside the GEMM loop (mcosb_sample_moments is the same pair as a stage call)
+        MCOSB_TRY(mcosb_dev_sample(ctx, sim0 + c0, nc, dX, false));
         MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, false));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, true));
         MCOSB_TRY(mcosb_dev_moments(ctx, nc, dX, plan->moments_kind, dmu + (size_t)c0 * N, dcov + (size_t)c0 * N * N,
-                                    nullptr, lwcoef ? lwcoef + 2 * (size_t)c0 : nullptr));
+                                    nullptr, lwcoef ? lwcoef + 2 * (size_t)c0 : nullptr, ctx->d_mu));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, false));
     }
     for (int i = 0; i < rp.ntr; ++i) {   // any list, in order (mcos.py:25-26)
@@ -121,6 +123,34 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, const RunPlan& rp, ui
         MCOSB_TRY(mark(MCOSB_STAGE_ERRORS, false));
     }
     return MCOSB_OK;
+}
+
+// Sampling + moment estimation exactly as mcosb_run chains them (draws centred by the true mean, sub-chunks of
+// RUN_CHUNK_BYTES), as a stage call: what a caller composes with mcosb_denoise / mcosb_markowitz / ... to reproduce
+// mcosb_run bit for bit.
+extern "C" int mcosb_sample_moments(mcosb_ctx* ctx, uint64_t sim_id0, int S, int kind, double* mu_hat, double* cov_hat,
+                                    double* shrink) {
+    MCOSB_CHECK_CTX(ctx);
+    if (S < 0 || !mu_hat || !cov_hat) return mcosb_fail(ctx, MCOSB_ERR_ARG, "bad argument to mcosb_sample_moments");
+    if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
+    const size_t N = ctx->N, T = ctx->T;
+    Staging st(ctx);
+    double *dmu, *dcov, *dsh;
+    MCOSB_TRY(st.out(mu_hat, (size_t)S * N, SL_STAGE_OUT0, &dmu));
+    MCOSB_TRY(st.out(cov_hat, (size_t)S * N * N, SL_STAGE_OUT1, &dcov));
+    MCOSB_TRY(st.out(shrink, (size_t)S, SL_STAGE_OUT2, &dsh));
+    if (S > 0) {
+        const int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, (size_t)RUN_CHUNK_BYTES / (T * N * sizeof(double))));
+        double* dX;
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * T * N, &dX));
+        for (int c0 = 0; c0 < S; c0 += CH) {
+            const int nc = std::min(CH, S - c0);
+            MCOSB_TRY(mcosb_dev_sample(ctx, sim_id0 + c0, nc, dX, false));
+            MCOSB_TRY(mcosb_dev_moments(ctx, nc, dX, kind, dmu + (size_t)c0 * N, dcov + (size_t)c0 * N * N,
+                                        dsh ? dsh + c0 : nullptr, nullptr, ctx->d_mu));
+        }
+    }
+    return st.finish();
 }
 
 extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id0, int S, double* err, int* status) {

@@ -158,7 +158,9 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
 #define T2_THREADS 128
 #define T2_BN 64
 #define T2_STAGE ((DM_BM + T2_BN) * DM_LD_MMAJOR)
-template <bool VEC>
+// ADDMU = false writes Y = Z L' = X - mu (the fused loop: its moments are taken from the pre-centred draws, mcosb_dev_moments
+// with `shift`), which also takes the mu loads out of the epilogue.
+template <bool VEC, bool ADDMU>
 __global__ void __launch_bounds__(T2_THREADS, 2)
 trmm2_kernel(const double* __restrict__ Z, const double* __restrict__ L, const double* __restrict__ mu, size_t M, int N,
              double* __restrict__ X) {
@@ -228,16 +230,17 @@ trmm2_kernel(const double* __restrict__ Z, const double* __restrict__ L, const d
             if (row < M) {
                 if (VEC && col + 1 < N) {
                     *reinterpret_cast<double2*>(X + row * N + col) =
-                        make_double2(acc[mb][nb][0] + mu[col], acc[mb][nb][1] + mu[col + 1]);
+                        ADDMU ? make_double2(acc[mb][nb][0] + mu[col], acc[mb][nb][1] + mu[col + 1])
+                              : make_double2(acc[mb][nb][0], acc[mb][nb][1]);
                 } else {
-                    if (col < N) X[row * N + col] = acc[mb][nb][0] + mu[col];
-                    if (col + 1 < N) X[row * N + col + 1] = acc[mb][nb][1] + mu[col + 1];
+                    if (col < N) X[row * N + col] = ADDMU ? acc[mb][nb][0] + mu[col] : acc[mb][nb][0];
+                    if (col + 1 < N) X[row * N + col + 1] = ADDMU ? acc[mb][nb][1] + mu[col + 1] : acc[mb][nb][1];
                 }
             }
         }
 }
 
-int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
+int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool add_mu) {
     if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
     if (S == 0) return MCOSB_OK;
     const int N = ctx->N, T = ctx->T;
@@ -251,7 +254,7 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");
     const bool vec = N % 2 == 0 && (uintptr_t)dZ % 16 == 0 && (uintptr_t)ctx->d_chol % 16 == 0 && (uintptr_t)dX % 16 == 0;
     static const bool one_cta = std::getenv("MCOSB_TRMM_256") != nullptr;   // the 128 x 128 / 256-thread variant (A/B runs)
-    if (one_cta) {
+    if (one_cta && add_mu) {
         const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
         dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
         if (vec) {
@@ -264,13 +267,16 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX) {
     } else {
         const size_t smem = (size_t)DM_STAGES * T2_STAGE * sizeof(double);
         dim3 g((N + T2_BN - 1) / T2_BN, (unsigned)row_tiles);
-        if (vec) {
-            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            trmm2_kernel<true><<<g, T2_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
-        } else {
-            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            trmm2_kernel<false><<<g, T2_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
-        }
+#define T2_LAUNCH(V, A)                                                                                               \
+    do {                                                                                                              \
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<V, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        trmm2_kernel<V, A><<<g, T2_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);                \
+    } while (0)
+        if (vec && add_mu) T2_LAUNCH(true, true);
+        else if (vec) T2_LAUNCH(true, false);
+        else if (add_mu) T2_LAUNCH(false, true);
+        else T2_LAUNCH(false, false);
+#undef T2_LAUNCH
     }
     MCOSB_LAUNCHED(ctx, MK_TRMM);
     return MCOSB_OK;
@@ -282,6 +288,6 @@ extern "C" int mcosb_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* X) 
     Staging st(ctx);
     double* dX;
     MCOSB_TRY(st.out(X, (size_t)S * ctx->T * ctx->N, SL_STAGE_OUT0, &dX));
-    MCOSB_TRY(mcosb_dev_sample(ctx, sim_id0, S, dX));
+    MCOSB_TRY(mcosb_dev_sample(ctx, sim_id0, S, dX, true));
     return st.finish();
 }

@@ -139,6 +139,15 @@ class Engine:
         self._check(self.lib.mcosb_moments(self.h, s, px, kind, pmu, pcov, psh))
         return mu, cov, sh
 
+    def sample_moments(self, n_sims, sim_id0=0, kind=_lib.MOMENTS_MUCOV, out_torch=False):
+        """(mu_hat, cov_hat, shrink) of simulations sim_id0 .. as mcosb_run forms them (draws kept on the device, centred by
+        the true mean): the stage call that composes with denoise / markowitz / ... to mcosb_run bit for bit."""
+        mu, pmu = self._out(out_torch, (n_sims, self.N))
+        cov, pcov = self._out(out_torch, (n_sims, self.N, self.N))
+        sh, psh = self._out(out_torch, (n_sims,))
+        self._check(self.lib.mcosb_sample_moments(self.h, ctypes.c_uint64(sim_id0), n_sims, kind, pmu, pcov, psh))
+        return mu, cov, sh
+
     def denoise(self, cov, n_observations=None, bandwidth=0.25):
         s = cov.shape[0]
         tt = _is_torch(cov)

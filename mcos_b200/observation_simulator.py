@@ -46,8 +46,7 @@ class _GpuObservationSimulator(AbstractObservationSimulator):
         if sim_id0 is None:
             sim_id0 = self._next_sim_id
             self._next_sim_id += n_sims
-        x = eng.sample(n_sims, sim_id0)
-        mu_hat, cov_hat, _ = eng.moments(x, self.kind)
+        mu_hat, cov_hat, _ = eng.sample_moments(n_sims, sim_id0, self.kind)   # the draws never leave the device
         return mu_hat, cov_hat
 
     def moments(self, x):

@@ -99,7 +99,7 @@ def _run_config(n, t, s, sim_name, moments_kind, denoise, optimizers, kinds, see
     assert (status == 0).all(), status
     x = eng.sample(s, sim_id0=100)
     # the GPU's own stage outputs (fused == stage by stage, bit for bit: tests/test_gpu_run.py)
-    mu_hat_gpu, cov_gpu, _ = eng.moments(x, moments_kind)
+    mu_hat_gpu, cov_gpu, _ = eng.sample_moments(s, 100, moments_kind)
     if denoise:
         cov_gpu, _ = eng.denoise(cov_gpu, t)
     # the oracle's

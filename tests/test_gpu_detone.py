@@ -49,8 +49,7 @@ def test_detone_in_the_fused_loop():
                                       [mb.DeNoiserCovarianceTransformer(), mb.DetoneCovarianceTransformer(1)])
     eng = Engine(40, 120, seed=9)
     eng.set_truth(mu, cov)
-    x = eng.sample(10)
-    _, c, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
+    _, c, _ = eng.sample_moments(10, 0, _lib.MOMENTS_MUCOV)     # sampling + moments as the fused loop runs them
     c, _ = eng.denoise(c, 120)
     c, _ = eng.detone(c, 1)
     w, _ = eng.hrp(c)

@@ -35,9 +35,14 @@ def test_run_equals_stage_by_stage_and_oracle(n, t, moments, denoise, err):
     plan = _plan(moments, denoise, [_lib.OPT_MARKOWITZ, _lib.OPT_HRP], err, wave=5)   # 3 ragged waves
     errs, status = eng.run(plan, s, sim_id0=3)
     assert (status == 0).all()
-    # the same simulations, one stage at a time through the C ABI
+    # the same simulations, one stage at a time through the C ABI.  mcosb_sample_moments is the sampling + moments stage as
+    # the fused loop runs it (draws kept centred by the true mean); the draws themselves (mcosb_sample) feed the oracle, and
+    # mcosb_moments on them agrees to rounding
     x = eng.sample(s, sim_id0=3)
-    mu_hat, cov_hat, _ = eng.moments(x, moments)
+    mu_hat, cov_hat, _ = eng.sample_moments(s, 3, moments)
+    mu_x, cov_x, _ = eng.moments(x, moments)
+    assert_allclose(mu_hat, mu_x, rtol=1e-12, atol=1e-15)
+    assert_allclose(cov_hat, cov_x, rtol=1e-11, atol=1e-12 * np.abs(cov_x).max())
     if denoise:
         cov_hat, _ = eng.denoise(cov_hat, t)
     wm, _ = eng.markowitz(mu_hat, cov_hat)
@@ -162,8 +167,7 @@ def test_user_plugins_run_on_the_host_around_the_gpu_stages():
     fused, _ = mb.simulate_errors(sim, s, [mb.HRPOptimizer()], mb.VarianceErrorEstimator(), [mb.DeNoiserCovarianceTransformer()])
     assert np.array_equal(errs[:, 1], fused[:, 0])                  # the built-in column is what the fused loop gives
     eng = get_engine(n, t, 0, 4)
-    x = eng.sample(s, 0)
-    _, cov_hat, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
+    _, cov_hat, _ = eng.sample_moments(s, 0, _lib.MOMENTS_MUCOV)
     cov_dn, _ = eng.denoise(cov_hat, t)
     ideal = InverseVariance().allocate(mu, cov)
     want = [oracle.err_variance(mu, cov, InverseVariance().allocate(None, c), ideal) for c in cov_dn]
@@ -216,8 +220,7 @@ def test_more_than_four_optimizers_and_risk_budget_in_the_fused_loop():
     first4, _ = mb.simulate_errors(sim, s, opts[:4], mb.VarianceErrorEstimator(), [mb.DeNoiserCovarianceTransformer()])
     assert np.array_equal(errs[:, :4], first4)
     eng = get_engine(n, t, 0, 8)
-    x = eng.sample(s, 0)
-    _, cov_hat, _ = eng.moments(x, _lib.MOMENTS_LEDOIT_WOLF)
+    _, cov_hat, _ = eng.sample_moments(s, 0, _lib.MOMENTS_LEDOIT_WOLF)
     cov_dn, _ = eng.denoise(cov_hat, t)
     w, _ = eng.risk_parity(cov_dn, budget)
     iw, _ = eng.risk_parity(cov[None], budget)
@@ -236,8 +239,7 @@ def test_transformer_lists_in_any_order():
     sim = mb.MuCovObservationSimulator(mu, cov, t, seed=6)
     eng = get_engine(n, t, 0, 6)
     eng.ensure_truth(mu, cov)
-    x = eng.sample(s, 0)
-    _, cov_hat, _ = eng.moments(x, _lib.MOMENTS_MUCOV)
+    _, cov_hat, _ = eng.sample_moments(s, 0, _lib.MOMENTS_MUCOV)
     ih, _ = eng.hrp(cov[None])
     for trs, stages in (([mb.DetoneCovarianceTransformer(1), mb.DeNoiserCovarianceTransformer()], "TD"),
                         ([mb.DeNoiserCovarianceTransformer(), mb.DetoneCovarianceTransformer(2), mb.DeNoiserCovarianceTransformer(0.3)], "DtD")):

@@ -9,6 +9,7 @@ import subprocess
 import sys
 
 rep, top = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
+only = sys.argv[3] if len(sys.argv) > 3 else ""      # substring of the kernel's function name
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 agg = collections.defaultdict(lambda: collections.Counter())
@@ -17,6 +18,12 @@ total = 0
 i = 0
 while i < len(rows):
     if rows[i] and rows[i][0] == "File Path":
+        fname = rows[i + 1][1] if len(rows[i + 1]) > 1 else ""
+        if only and only not in fname:
+            i += 3
+            while i < len(rows) and not (rows[i] and rows[i][0] == "File Path"):
+                i += 1
+            continue
         fp, hdr = rows[i][1].split("/")[-1], rows[i + 2]
         col = {h: k for k, h in enumerate(hdr)}
         j = i + 3
