@@ -19,7 +19,7 @@ enum ScratchSlot {
     SL_MK_L, SL_MK_W, SL_MK_ITERS,
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
     SL_NCO_W, SL_NCO_LABELS, SL_NCO_WORK, SL_NCO_E,
-    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2, SL_NCO_CENTERS, SL_S2_ZP, SL_S2_ZC,
+    SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2, SL_NCO_CENTERS, SL_S2_ZP, SL_S2_ZC, SL_S3_V, SL_S3_W, SL_S3_GT, SL_S3_ZP,
     SL_COUNT
 };
 
@@ -58,6 +58,8 @@ enum KernelId {
     MK_Q2BACK,
     MK_HRP_GRAM,
     MK_HRP_PRIM,
+    MK_SY2SB_PANEL,
+    MK_SY2SB_PASS,
     MK_COUNT
 };
 static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
@@ -94,7 +96,9 @@ static const char* const MCOSB_KERNEL_NAMES[MK_COUNT] = {
     "sb2st",
     "q2back",
     "hrp_gram",
-    "hrp_prim"
+    "hrp_prim",
+    "sy2sb_panel",
+    "sy2sb_pass"
 };
 
 struct mcosb_ctx {

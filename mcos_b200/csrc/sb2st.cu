@@ -540,22 +540,34 @@ int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, 
 // pay (the pass is bound by shared-memory / shuffle issue and DMMA dependency latency, not by the barrier), so the old
 // kernel stays the default wherever it runs and the new one takes N = 697 .. 1024, where the alternative is the one-stage
 // kernel at 527 us per matrix (N = 1000: 183 us).  MCOSB_SY2SB_OLD=0 forces the new kernel everywhere (A/B runs, tests).
-static bool sbr_use_old_stage1(int N) {
+// MCOSB_STAGE1 = 1 | 2 | 3 forces sy2sb.cu (N <= 696 only) | sy2sb2.cu | sy2sb3.cu (batched multi-kernel form) for A/B runs
+// and tests; MCOSB_SY2SB_OLD (round 2, first session) is still honoured: 1 -> kind 1, 0 -> kind 2.
+int sbr_stage1_kind(int N) {
     static int v = -2;
-    if (v == -2) { const char* e = getenv("MCOSB_SY2SB_OLD"); v = e ? (atoi(e) ? 1 : 0) : -1; }
-    if (v >= 0) return v == 1 && N <= 696;
-    return N <= 696;
+    if (v == -2) {
+        const char* e = getenv("MCOSB_STAGE1");
+        const char* o = getenv("MCOSB_SY2SB_OLD");
+        v = e ? atoi(e) : (o ? (atoi(o) ? 1 : 2) : -1);
+    }
+    if (v == 1) return N <= 696 ? 1 : 2;
+    if (v == 2 || v == 3) return v;
+    return SBR_STAGE1_DEFAULT(N);
 }
 
 bool mcosb_sbr_supported(mcosb_ctx* ctx) {
     const int N = ctx->N;
     extern size_t sbr_stage1_smem(int N);
-    const bool stage1 = sbr_use_old_stage1(N) ? (sbr_stage1_smem(N) <= (size_t)ctx->smem_optin) : sbr2_supported(ctx);
+    const int kind = sbr_stage1_kind(N);
+    const bool stage1 = kind == 1 ? (sbr_stage1_smem(N) <= (size_t)ctx->smem_optin)
+                                  : (kind == 2 ? sbr2_supported(ctx) : sbr3_supported(ctx));
     const size_t q2b = ((size_t)(N + 8) * Q2B_V + 2 * (size_t)(N + 8)) * sizeof(double);
     return N >= SBR_B + 2 && N <= 1024 && stage1 && q2b <= (size_t)ctx->smem_optin &&
            (size_t)(N + 16) * 16 * sizeof(double) + 1024 <= (size_t)ctx->smem_optin;
 }
 
 int mcosb_launch_stage1(mcosb_ctx* ctx, int S, double* A, double* tau) {
-    return sbr_use_old_stage1(ctx->N) ? mcosb_launch_sy2sb(ctx, S, A, tau) : mcosb_launch_sy2sb2(ctx, S, A, tau);
+    const int kind = sbr_stage1_kind(ctx->N);
+    if (kind == 1) return mcosb_launch_sy2sb(ctx, S, A, tau);
+    if (kind == 2) return mcosb_launch_sy2sb2(ctx, S, A, tau);
+    return mcosb_launch_sy2sb3(ctx, S, A, tau);
 }

@@ -6,12 +6,19 @@
 #include "common.cuh"
 
 #define SBR_B 8
+#ifndef SBR_STAGE1_DEFAULT
+#define SBR_STAGE1_DEFAULT(N) ((N) <= 696 ? 1 : 2)   // which dense -> band kernel serves size N by default
+#endif
 #define SBR_MIN_N 128   // below this the one-stage kernels are used (mcosb_dev_eig_prepare)
 
 // Each returns 1 if launched, 0 if the problem size is outside its range (nothing launched), < 0 on error.
 int mcosb_launch_sy2sb(mcosb_ctx* ctx, int S, double* A, double* tau);    // round-1 kernel (N <= 696), MCOSB_SY2SB_OLD=1
 int mcosb_launch_sy2sb2(mcosb_ctx* ctx, int S, double* A, double* tau);   // two matrices per SM / N <= 1024 (sy2sb2.cu)
 bool sbr2_supported(mcosb_ctx* ctx);
+int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau);   // batched multi-kernel form (sy2sb3.cu), N <= 1024
+bool sbr3_supported(mcosb_ctx* ctx);
+size_t sbr3_scratch_bytes(int N);
+int sbr_stage1_kind(int N);   // 1 one CTA per matrix (sy2sb.cu), 2 sy2sb2.cu, 3 batched (sy2sb3.cu)
 int mcosb_launch_stage1(mcosb_ctx* ctx, int S, double* A, double* tau);       // the one in use
 int mcosb_launch_sb2st(mcosb_ctx* ctx, int S, const double* A, double* d, double* e, double* Q2);
 int mcosb_launch_q2back(mcosb_ctx* ctx, int S, const double* Q2, const int* nf, double* Wy);

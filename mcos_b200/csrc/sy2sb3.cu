@@ -1,0 +1,579 @@
+// D2 (fourth generation), stage 1 of the two-stage tridiagonalisation as a BATCHED, multi-kernel band reduction.
+//
+// sy2sb_kernel keeps one matrix per SM for its whole reduction: the per-panel chain (panel update -> Householder QR ->
+// trailing pass -> W) is serial inside a matrix, the CTA owns all of the SM's registers and shared memory, so nothing else is
+// resident to hide the chain and the DMMA pipe idles 74 % of the time (profiles/kernels_r02.md).  Here the same mathematics
+// (np.linalg.eigh's front end, covariance_transformer.py:105) is cut at the panel boundaries into two kernels that each run
+// over ALL matrices of the wave, so the latency of one matrix's chain hides behind the other thousands:
+//
+//   for each panel p (columns j1 .. j1+7, R0 = j1 + 8):
+//     s3_panel_kernel   one CTA per matrix, one thread per row (RPT rows each):
+//         W_{p-1} = Y - 1/2 V (T' V' Y),  Y = Z T,  Z = sum of the partial products the previous pass left      (p > 0)
+//         panel columns brought up to date with (V_{p-1}, W_{p-1}); rows j1 .. j1+7 are final (the band)
+//         Householder QR of the rows below the band: R -> band, reflectors -> row j1+c of the upper triangle, V_p, tau
+//     s3_pass_kernel    one CTA of 4 warps per 64 x 64 tile of the trailing LOWER triangle (grid: tiles x matrices):
+//         tile -= V_{p-1} W_{p-1}' + W_{p-1} V_{p-1}'      (4 DMMA.8x8x4 per 8 x 8 block, the tile is the C fragment)
+//         store tile
+//         Z[rows] += tile  * V_p[cols]                      (2 DMMA, C fragment reused as A operand, k permuted)
+//         Z[cols] += tile' * V_p[rows]  (strictly lower)    (2 DMMA, block transposed across the warp by 4 shuffles)
+//       A warp holds 16 rows x 64 columns = 16 blocks, all loaded up front (16 independent 16-byte loads per thread, then 16
+//       independent DMMA chains), so neither the L2 / HBM latency nor the DMMA dependency latency is exposed the way it is
+//       in the one-CTA kernel's ring of two tiles.  Row sums stay in registers across the tile; the column sums of the 4
+//       warps are folded through shared memory.  Both go to a slot of the per-matrix partial array Zpart[slot][N][8]:
+//       row block R receives slot J from tile (R, J), J <= R, and slot I + 1 from tile (I, R), I >= R -- every (slot <= nT,
+//       row) pair is written exactly once per pass, and the panel kernel adds the nT + 1 slots in index order: no atomics,
+//       bit-reproducible.
+//
+// Traffic per matrix: the trailing triangle read + written once per panel, 8 N^3 / 24 B = 41.7 MB at N = 500, plus the
+// partial sums and panel arrays (~20 %); at 6.5 TB/s that is ~7.5 us per 500 x 500 matrix against 4.5 us of DMMA work: this
+// form is HBM-bound where the one-CTA form was latency-bound at 17.9 us.  Output layout (band in the lower 9 diagonals,
+// reflectors in the rows of the upper triangle, tau) is the one sb2st_kernel / backtransform_kernel read.
+#include "common.cuh"
+#include "dmma.cuh"
+#include "sbr.cuh"
+#include <algorithm>
+
+#define S3_TILE 64
+#define S3_LDK 68      // k-major column operands [8][S3_LDK]: 4 * t + g distinct banks for the 8-byte fragment loads
+#define S3_LDC 72      // k-major column sums per warp [8][S3_LDC]
+#define S3_PASS_THREADS 128
+#define S3_PANEL_WARPS 8
+
+__device__ __forceinline__ double s3_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ double s3_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double h = 0.5 * x;
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    r = fma(r, fma(-h * r, r, 0.5), r);
+    return r;
+}
+
+// Sum 8 per-lane values over the 32 lanes (halving butterfly, 9 shuffles); lane 4 i ends up owning the total of value i.
+__device__ __forceinline__ double s3_reduce8(double (&v)[8], int lane) {
+    double a4[4], a2[2], a1;
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double send = up ? v[q] : v[q + 4];
+            const double keep = up ? v[q + 4] : v[q];
+            a4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double send = up ? a4[q] : a4[q + 2];
+            const double keep = up ? a4[q + 2] : a4[q];
+            a2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+        const double send = up ? a2[0] : a2[1];
+        const double keep = up ? a2[1] : a2[0];
+        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    return a1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Panel kernel.  Row i = j1 + tid + NT r of matrix s; rho = i - R0 = tid - 8 + NT r is its index below the band.
+// Vc = V_{p-1} and Zp = partial products of the previous pass (read), Wc = W_{p-1} (written), Vn = V_p (written),
+// GT = [64 strictly-upper entries of V'V | 8 tau] of the panel whose W is still to be formed (read, then replaced).
+template <int RPT>
+__global__ void __launch_bounds__(S3_PANEL_WARPS * 32, (RPT <= 2 ? 2 : 1))
+s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ tauall, const double* __restrict__ Vc_all,
+                double* __restrict__ Wc_all, double* __restrict__ Vn_all, double* __restrict__ GT_all,
+                const double* __restrict__ Zp_all, int nslot, int nused) {
+    constexpr int NW = S3_PANEL_WARPS, NT = NW * 32;
+    __shared__ __align__(16) double stV[NW][32 * 8];
+    __shared__ __align__(16) double stY[NW][32 * 8];
+    __shared__ double partM[NW * 64], M0[64], Mm[64], Gm[64], tauS[8], red[2 * NW * 8], rowc[16], pv[64], pw[64];
+
+    const int s = blockIdx.x;
+    double* A = Aall + (size_t)s * N * N;
+    double* tau = tauall + (size_t)s * N;
+    const double* Vc = Vc_all + (size_t)s * N * 8;
+    double* Wc = Wc_all + (size_t)s * N * 8;
+    double* Vn = Vn_all + (size_t)s * N * 8;
+    double* GT = GT_all + (size_t)s * 72;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const bool first = (j1 == 0);
+    const int R0 = j1 + SBR_B;
+    const int ncols = min(SBR_B, N - j1);
+    const bool last = (N - R0 < 2);
+
+    double v[RPT][8], wv[RPT][8];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[r][c] = wv[r][c] = 0.0;
+
+    if (first) {
+        for (int i = tid; i < N; i += NT) tau[i] = 0.0;
+    } else {
+        // ---- W of the previous panel: Y U = Z, M0 = V' Y, U' M = M0, W = Y - 1/2 V M; U = T^-1 = striu(V'V) + diag(1/tau) ----
+        if (tid < 64) Gm[tid] = GT[tid];
+        if (tid < 8) tauS[tid] = GT[64 + tid];
+        __syncthreads();
+        double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = j1 + tid + NT * r;
+            if (i < N) {
+                double z[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x) z[x] = 0.0;
+                const double* zp = Zp_all + ((size_t)s * nslot * N + i) * 8;
+                for (int sl = 0; sl < nused; ++sl) {
+                    const double2* q2 = reinterpret_cast<const double2*>(zp + (size_t)sl * N * 8);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const double2 a = __ldcg(q2 + x);
+                        z[2 * x] += a.x;
+                        z[2 * x + 1] += a.y;
+                    }
+                }
+                const double2* vq = reinterpret_cast<const double2*>(Vc + (size_t)i * 8);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const double2 a = __ldcg(vq + x);
+                    v[r][2 * x] = a.x;
+                    v[r][2 * x + 1] = a.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {       // Y U = Z
+                    double a = z[c];
+#pragma unroll
+                    for (int x = 0; x < c; ++x) a = fma(-wv[r][x], Gm[x * 8 + c], a);
+                    wv[r][c] = a * tauS[c];
+                }
+            }
+            // this warp's 32 rows of V and Y -> shared memory, then M0 += V' Y as 8 DMMAs (k = rows, 4 at a time)
+            __syncwarp();
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                *reinterpret_cast<double2*>(&stV[w][lane * 8 + 2 * x]) = make_double2(v[r][2 * x], v[r][2 * x + 1]);
+                *reinterpret_cast<double2*>(&stY[w][lane * 8 + 2 * x]) = make_double2(wv[r][2 * x], wv[r][2 * x + 1]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dmma_884(m0, m1, stV[w][(4 * q + t) * 8 + g], stY[w][(4 * q + t) * 8 + g]);
+        }
+        partM[w * 64 + g * 8 + 2 * t] = m0;
+        partM[w * 64 + g * 8 + 2 * t + 1] = m1;
+        __syncthreads();
+        if (tid < 64) {
+            double a = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) a += partM[ww * 64 + tid];
+            M0[tid] = a;
+        }
+        __syncthreads();
+        if (tid < 8) {                               // U' M = M0, column tid of M
+            const int c = tid;
+            double mcol[8];
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) {
+                double a = M0[c2 * 8 + c];
+#pragma unroll
+                for (int x = 0; x < c2; ++x) a = fma(-Gm[x * 8 + c2], mcol[x], a);
+                mcol[c2] = a * tauS[c2];
+                Mm[c2 * 8 + c] = mcol[c2];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = j1 + tid + NT * r;
+            if (i < N) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) a = fma(v[r][x], Mm[x * 8 + c], a);
+                    wv[r][c] = fma(-0.5, a, wv[r][c]);
+                }
+                double2* wq = reinterpret_cast<double2*>(Wc + (size_t)i * 8);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) __stcg(wq + x, make_double2(wv[r][2 * x], wv[r][2 * x + 1]));
+            }
+        }
+        if (tid < 8) {                               // rows j1 .. j1+7: the column side of the panel's own update
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                pv[tid * 8 + x] = v[0][x];
+                pw[tid * 8 + x] = wv[0][x];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- panel columns j1 .. j1+7, rows j1 .. N-1: load, bring up to date with (V_{p-1}, W_{p-1}) ------------------------
+    double p[RPT][8];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = j1 + tid + NT * r;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p[r][c] = 0.0;
+        if (i < N) {
+            const double* row = A + (size_t)i * N + j1;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < ncols && j1 + c <= i) p[r][c] = __ldcg(row + c);
+            if (!first) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double vi = v[r][k], wi = wv[r][k];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) p[r][c] = fma(-vi, pw[c * 8 + k], fma(-wi, pv[c * 8 + k], p[r][c]));
+                }
+            }
+            if (i < R0 || last) {          // diagonal block of the band (or nothing left to factorise): final
+                double* wrow = A + (size_t)i * N + j1;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < ncols && j1 + c <= i) __stcg(wrow + c, p[r][c]);
+            }
+        }
+    }
+    if (last) {
+        // nothing left to eliminate; at most one more column (the last diagonal element) needs the update
+        if (N - R0 == 1 && tid == 8 && !first) {     // tid 8, r = 0 holds row R0 = N - 1
+            const int i = N - 1;
+            double a = __ldcg(A + (size_t)i * N + i);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = fma(-2.0 * v[0][k], wv[0][k], a);
+            __stcg(A + (size_t)i * N + i, a);
+        }
+        return;
+    }
+
+    // ---- Householder QR of the rows >= R0 of the panel --------------------------------------------------------------------
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int par = c & 1;
+        double pr[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) pr[cc] = 0.0;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int rho = tid - 8 + NT * r;
+            if (rho > c) {                 // rows beyond N hold zeros
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) pr[cc] = fma(p[r][c], p[r][cc], pr[cc]);
+            }
+        }
+        const double tot_lane = s3_reduce8(pr, lane);
+        if (t == 0) red[(par * NW + w) * 8 + g] = tot_lane;
+        if (tid == c + 8) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) rowc[par * 8 + cc] = p[0][cc];
+        }
+        __syncthreads();
+        double tot[8];
+        {
+            const int cc = lane & 7, jj = lane >> 3;
+            double a = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < NW; ww += 4) a += red[(par * NW + ww + jj) * 8 + cc];
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) tot[c2] = __shfl_sync(0xffffffffu, a, c2);
+        }
+        const double alpha = rowc[par * 8 + c];
+        const double xn2 = tot[c];
+        double tc = 0.0, scale = 0.0, beta = alpha;
+        if (xn2 > 1e-280) {
+            const double n2 = fma(alpha, alpha, xn2);
+            const double rs = s3_rsqrt(n2), nrm = n2 * rs, aa = fabs(alpha);
+            beta = -copysign(nrm, alpha);
+            tc = fma(aa, rs, 1.0);                               // (beta - alpha) / beta
+            scale = copysign(s3_rcp(aa + nrm), alpha);          // 1 / (alpha - beta)
+        }
+#pragma unroll
+        for (int cc = c + 1; cc < 8; ++cc) {
+            const double wvv = tc * fma(scale, tot[cc], rowc[par * 8 + cc]);
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int rho = tid - 8 + NT * r;
+                if (rho > c) p[r][cc] = fma(-(p[r][c] * scale), wvv, p[r][cc]);
+                else if (rho == c) p[r][cc] -= wvv;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int rho = tid - 8 + NT * r;
+            if (rho > c) p[r][c] *= scale;
+            else if (rho == c) p[r][c] = beta;
+        }
+        if (tid == 64) {                   // G[x][c] = v_x . v_c = v_x[c] + scale * (v_x . x_c below row c), x < c
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+                if (x < c) GT[x * 8 + c] = fma(scale, tot[x], rowc[par * 8 + x]);
+            GT[64 + c] = tc;
+            tau[j1 + c] = tc;
+        }
+    }
+    // ---- R to the band, reflectors to the upper triangle and to V_p ------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int rho = tid - 8 + NT * r;
+        const int i = R0 + rho;
+        if (rho >= 0 && i < N) {
+            double vrow[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (rho <= c) {
+                    __stcg(A + (size_t)i * N + j1 + c, p[r][c]);
+                    vrow[c] = (rho == c) ? 1.0 : 0.0;
+                } else {
+                    vrow[c] = p[r][c];
+                    A[(size_t)(j1 + c) * N + i] = p[r][c];
+                }
+            }
+            double2* vq = reinterpret_cast<double2*>(Vn + (size_t)i * 8);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) __stcg(vq + x, make_double2(vrow[2 * x], vrow[2 * x + 1]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Pass kernel: tile (I, J), I >= J, of the trailing matrix that starts at (R0, R0).  Warp w: rows i00 + 16 w + [0, 16).
+// MASKED tiles (on the diagonal, overhanging N, or N odd) take element-wise predicates and 8-byte accesses.
+template <bool FIRST, bool MASKED>
+__device__ __forceinline__ void s3_pass_tile(double* __restrict__ A, int N, int i00, int j00, const double* __restrict__ Vc,
+                                             const double* __restrict__ Wc, const double* __restrict__ Vn,
+                                             double* __restrict__ zrow, const double* sV, const double* sW,
+                                             const double* sVn, double* sZc, int w, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const int ib0 = i00 + 16 * w;
+    // ---- the warp's 16 x 64 of the tile: every load in flight before anything is used ----------------------------------
+    double c[2][8][2];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        const int i = ib0 + 8 * rb + g;
+        const double* row = A + (size_t)i * N + j00 + 2 * t;
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {
+            if (MASKED) {
+                const int j = j00 + 8 * cb + 2 * t;
+                c[rb][cb][0] = (i < N && j <= i) ? __ldcg(row + 8 * cb) : 0.0;
+                c[rb][cb][1] = (i < N && j + 1 <= i) ? __ldcg(row + 8 * cb + 1) : 0.0;
+            } else {
+                const double2 v2 = __ldcg(reinterpret_cast<const double2*>(row + 8 * cb));
+                c[rb][cb][0] = v2.x;
+                c[rb][cb][1] = v2.y;
+            }
+        }
+    }
+    // ---- row-side operands straight from the panel arrays (each used by this warp only) ---------------------------------
+    double av[2][4], vni[2][2];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        const int i = ib0 + 8 * rb + g;
+        const bool in = !MASKED || i < N;
+        if (!FIRST) {
+            av[rb][0] = in ? -__ldg(Vc + (size_t)i * 8 + t) : 0.0;
+            av[rb][1] = in ? -__ldg(Vc + (size_t)i * 8 + 4 + t) : 0.0;
+            av[rb][2] = in ? -__ldg(Wc + (size_t)i * 8 + t) : 0.0;
+            av[rb][3] = in ? -__ldg(Wc + (size_t)i * 8 + 4 + t) : 0.0;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ir = ib0 + 8 * rb + 4 * h + t;
+            vni[rb][h] = (!MASKED || ir < N) ? __ldg(Vn + (size_t)ir * 8 + g) : 0.0;
+        }
+    }
+    __syncthreads();   // column operands staged by the CTA are in shared memory
+    double zi[2][2];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) zi[rb][0] = zi[rb][1] = 0.0;
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) {
+        const int jb = j00 + 8 * cb;
+        double zc0 = 0.0, zc1 = 0.0;
+        // blocks entirely above the diagonal or below row N contribute nothing (warp-uniform)
+        const double2 vnj = *reinterpret_cast<const double2*>(sVn + g * S3_LDK + 8 * cb + 2 * t);
+        double bw0 = 0.0, bw1 = 0.0, bv0 = 0.0, bv1 = 0.0;
+        if (!FIRST) {
+            bw0 = sW[t * S3_LDK + 8 * cb + g];
+            bw1 = sW[(4 + t) * S3_LDK + 8 * cb + g];
+            bv0 = sV[t * S3_LDK + 8 * cb + g];
+            bv1 = sV[(4 + t) * S3_LDK + 8 * cb + g];
+        }
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+            const int ib = ib0 + 8 * rb;
+            if (!MASKED || (jb <= ib && ib < N)) {
+                const int i = ib + g, j = jb + 2 * t;
+                double u0 = c[rb][cb][0], u1 = c[rb][cb][1];
+                if (!FIRST) {
+                    dmma_884(u0, u1, av[rb][0], bw0);
+                    dmma_884(u0, u1, av[rb][1], bw1);
+                    dmma_884(u0, u1, av[rb][2], bv0);
+                    dmma_884(u0, u1, av[rb][3], bv1);
+                    double* dst = A + (size_t)i * N + j;
+                    if (MASKED) {
+                        const bool p0 = i < N && j <= i, p1 = i < N && j + 1 <= i;
+                        u0 = p0 ? u0 : 0.0;
+                        u1 = p1 ? u1 : 0.0;
+                        if (p0) __stcg(dst, u0);
+                        if (p1) __stcg(dst + 1, u1);
+                    } else {
+                        __stcg(reinterpret_cast<double2*>(dst), make_double2(u0, u1));
+                    }
+                }
+                // Z[rows] += block * V_p[cols]: k = block columns, permuted (2 t | 2 t + 1) to match the C fragment
+                dmma_884(zi[rb][0], zi[rb][1], u0, vnj.x);
+                dmma_884(zi[rb][0], zi[rb][1], u1, vnj.y);
+                // Z[cols] += block' * V_p[rows], strictly lower part: B operand element (k = t -> row 4 h + t, n = g -> column g)
+                double l0 = u0, l1 = u1;
+                if (MASKED) {
+                    l0 = (j < i) ? u0 : 0.0;
+                    l1 = (j + 1 < i) ? u1 : 0.0;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int src = 4 * (4 * h + t) + (g >> 1);
+                    const double e0 = __shfl_sync(0xffffffffu, l0, src);
+                    const double e1 = __shfl_sync(0xffffffffu, l1, src);
+                    dmma_884(zc0, zc1, vni[rb][h], (g & 1) ? e1 : e0);
+                }
+            }
+        }
+        *reinterpret_cast<double2*>(sZc + (w * 8 + g) * S3_LDC + 8 * cb + 2 * t) = make_double2(zc0, zc1);
+    }
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        const int i = ib0 + 8 * rb + g;
+        if (!MASKED || i < N)
+            __stcg(reinterpret_cast<double2*>(zrow + (size_t)i * 8 + 2 * t), make_double2(zi[rb][0], zi[rb][1]));
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(S3_PASS_THREADS, 3)
+s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restrict__ Vc_all, const double* __restrict__ Wc_all,
+               const double* __restrict__ Vn_all, double* __restrict__ Zp_all, int nslot) {
+    __shared__ __align__(16) double sV[8 * S3_LDK], sW[8 * S3_LDK], sVn[8 * S3_LDK];
+    __shared__ __align__(16) double sZc[4 * 8 * S3_LDC];
+    const int s = blockIdx.y;
+    int I, J;
+    dm_tile_ij(blockIdx.x, I, J);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double* A = Aall + (size_t)s * N * N;
+    const double* Vc = Vc_all + (size_t)s * N * 8;
+    const double* Wc = Wc_all + (size_t)s * N * 8;
+    const double* Vn = Vn_all + (size_t)s * N * 8;
+    double* zrow = Zp_all + ((size_t)s * nslot + J) * N * 8;
+    double* zcol = Zp_all + ((size_t)s * nslot + I + 1) * N * 8;
+    const int i00 = R0 + S3_TILE * I, j00 = R0 + S3_TILE * J;
+
+    // column operands of the tile, k-major, zero beyond N
+    for (int idx = tid; idx < S3_TILE * 8; idx += S3_PASS_THREADS) {
+        const int jl = idx >> 3, k = idx & 7;
+        const bool in = j00 + jl < N;
+        sVn[k * S3_LDK + jl] = in ? __ldg(Vn + (size_t)j00 * 8 + idx) : 0.0;
+        if (!FIRST) {
+            sV[k * S3_LDK + jl] = in ? __ldg(Vc + (size_t)j00 * 8 + idx) : 0.0;
+            sW[k * S3_LDK + jl] = in ? __ldg(Wc + (size_t)j00 * 8 + idx) : 0.0;
+        }
+    }
+    const bool masked = (I == J) || (i00 + S3_TILE > N) || (N & 1);
+    if (masked) s3_pass_tile<FIRST, true>(A, N, i00, j00, Vc, Wc, Vn, zrow, sV, sW, sVn, sZc, w, lane);
+    else s3_pass_tile<FIRST, false>(A, N, i00, j00, Vc, Wc, Vn, zrow, sV, sW, sVn, sZc, w, lane);
+    __syncthreads();
+    // column sums of the 4 warps, in warp order
+    for (int idx = tid; idx < S3_TILE * 8; idx += S3_PASS_THREADS) {
+        const int jl = idx >> 3, k = idx & 7;
+        if (j00 + jl < N) {
+            double a = sZc[(0 * 8 + k) * S3_LDC + jl];
+#pragma unroll
+            for (int ww = 1; ww < 4; ++ww) a += sZc[(ww * 8 + k) * S3_LDC + jl];
+            __stcg(zcol + (size_t)j00 * 8 + idx, a);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+static int s3_nslot(int N) { return (N - SBR_B + S3_TILE - 1) / S3_TILE + 1; }
+
+// extra device bytes per matrix (wave sizing in run.cu)
+size_t sbr3_scratch_bytes(int N) { return ((size_t)(3 + s3_nslot(N)) * N * 8 + 72) * sizeof(double); }
+
+bool sbr3_supported(mcosb_ctx* ctx) {
+    const int N = ctx->N;
+    return N >= SBR_B + 2 && N <= 1024;
+}
+
+// Returns 1 if launched, 0 if N is outside the range of these kernels.
+int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
+    const int N = ctx->N;
+    if (!sbr3_supported(ctx)) return 0;
+    if (S > 32768) {                     // the matrix index is blockIdx.y of the pass
+        for (int s0 = 0; s0 < S; s0 += 32768) {
+            const int rc = mcosb_launch_sy2sb3(ctx, std::min(32768, S - s0), A + (size_t)s0 * N * N, tau + (size_t)s0 * N);
+            if (rc != 1) return rc;
+        }
+        return 1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {                     // three 32 KB CTAs per SM need more than the default carve-out
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+        attr_set = true;
+    }
+    const int nslot = s3_nslot(N);
+    double *Vb, *Wb, *GT, *Zp;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S3_V, (size_t)2 * S * N * 8, &Vb));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S3_W, (size_t)S * N * 8, &Wb));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S3_GT, (size_t)S * 72, &GT));
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_S3_ZP, (size_t)S * nslot * N * 8, &Zp));
+    double* Vbuf[2] = {Vb, Vb + (size_t)S * N * 8};
+    static const int stop_after = getenv("MCOSB_S3_STOP") ? atoi(getenv("MCOSB_S3_STOP")) : -1;   // debugging: launches to run
+    int launched = 0;
+    const int rpt = (N + S3_PANEL_WARPS * 32 - 1) / (S3_PANEL_WARPS * 32);
+    int nused = 0;
+    for (int p = 0, j1 = 0;; ++p, j1 += SBR_B) {
+        const int R0 = j1 + SBR_B;
+        const bool last = (N - R0 < 2);
+        double* Vc = Vbuf[(p + 1) & 1];
+        double* Vn = Vbuf[p & 1];
+        if (stop_after >= 0 && launched >= stop_after) break;
+#define S3_PANEL(RPT)                                                                                                  \
+        s3_panel_kernel<RPT><<<S, S3_PANEL_WARPS * 32, 0, ctx->stream>>>(A, N, j1, tau, Vc, Wb, Vn, GT, Zp, nslot, nused)
+        if (rpt <= 1) S3_PANEL(1);
+        else if (rpt == 2) S3_PANEL(2);
+        else if (rpt == 3) S3_PANEL(3);
+        else S3_PANEL(4);
+#undef S3_PANEL
+        MCOSB_LAUNCHED(ctx, MK_SY2SB_PANEL);
+        ++launched;
+        if (last) break;
+        if (stop_after >= 0 && launched >= stop_after) break;
+        const int m = N - R0;
+        const int nT = (m + S3_TILE - 1) / S3_TILE;
+        const dim3 grid(nT * (nT + 1) / 2, S);
+        if (p == 0) s3_pass_kernel<true><<<grid, S3_PASS_THREADS, 0, ctx->stream>>>(A, N, R0, Vc, Wb, Vn, Zp, nslot);
+        else s3_pass_kernel<false><<<grid, S3_PASS_THREADS, 0, ctx->stream>>>(A, N, R0, Vc, Wb, Vn, Zp, nslot);
+        MCOSB_LAUNCHED(ctx, MK_SY2SB_PASS);
+        ++launched;
+        nused = nT + 1;
+    }
+    return 1;
+}
