@@ -33,10 +33,6 @@
 #include "sbr.cuh"
 #include <algorithm>
 
-#define S3_TILE 64
-#define S3_LDK 68      // k-major column operands [8][S3_LDK]: 4 * t + g distinct banks for the 8-byte fragment loads
-#define S3_LDC 72      // k-major column sums per warp [8][S3_LDC]
-#define S3_PASS_THREADS 128
 #define S3_PANEL_WARPS 8
 
 __device__ __forceinline__ double s3_rcp(double x) {
@@ -95,7 +91,7 @@ template <int RPT>
 __global__ void __launch_bounds__(S3_PANEL_WARPS * 32, (RPT <= 2 ? 2 : 1))
 s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ tauall, const double* __restrict__ Vc_all,
                 double* __restrict__ Wc_all, double* __restrict__ Vn_all, double* __restrict__ GT_all,
-                const double* __restrict__ Zp_all, int nslot, int nused) {
+                const double* __restrict__ Zp_all, int nslot, int nused, int tr) {
     constexpr int NW = S3_PANEL_WARPS, NT = NW * 32;
     __shared__ __align__(16) double stV[NW][32 * 8];
     __shared__ __align__(16) double stY[NW][32 * 8];
@@ -136,9 +132,11 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
                 double z[8];
 #pragma unroll
                 for (int x = 0; x < 8; ++x) z[x] = 0.0;
+                // the previous pass left the row-side sum of this row in slot 0 and the column-side sums of the tile rows
+                // I >= R = (i - j1) / tr in slots I + 1 (tr = rows per tile row of the pass)
                 const double* zp = Zp_all + ((size_t)s * nslot * N + i) * 8;
-                for (int sl = 0; sl < nused; ++sl) {
-                    const double2* q2 = reinterpret_cast<const double2*>(zp + (size_t)sl * N * 8);
+                for (int sl = (i - j1) / tr; sl < nused; ++sl) {
+                    const double2* q2 = reinterpret_cast<const double2*>(zp + (size_t)(sl == (i - j1) / tr ? 0 : sl) * N * 8);
 #pragma unroll
                     for (int x = 0; x < 4; ++x) {
                         const double2 a = __ldcg(q2 + x);
@@ -353,75 +351,112 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Pass kernel: tile (I, J), I >= J, of the trailing matrix that starts at (R0, R0).  Warp w: rows i00 + 16 w + [0, 16).
-// MASKED tiles (on the diagonal, overhanging N, or N odd) take element-wise predicates and 8-byte accesses.
-template <bool FIRST, bool MASKED>
-__device__ __forceinline__ void s3_pass_tile(double* __restrict__ A, int N, int i00, int j00, const double* __restrict__ Vc,
-                                             const double* __restrict__ Wc, const double* __restrict__ Vn,
-                                             double* __restrict__ zrow, const double* sV, const double* sW,
-                                             const double* sVn, double* sZc, int w, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    const int ib0 = i00 + 16 * w;
-    // ---- the warp's 16 x 64 of the tile: every load in flight before anything is used ----------------------------------
-    double c[2][8][2];
+// Pass kernel.  One CTA of S3_PW warps per (matrix, tile row I of S3_TR = 16 S3_PW rows): it walks the trailing matrix that
+// starts at (R0, R0) from column R0 to the diagonal in steps of 32 columns; warp w owns rows i00 + 16 w + [0, 16) = 2 x 4 blocks
+// of 8 x 8 per step.  Global -> shared with cp.async through a ring of two stages, issued one full step ahead: a thread copies
+// exactly the eight 16-byte pieces it will read back itself (its C fragments), so the tile data needs no barrier; the column
+// operands of the step (V_{p-1}, W_{p-1}, V_p rows j0 .. j0+31) are shared by the warps.  Two barriers per step: "stage k
+// has landed", and "column sums of the warps are in shared memory / stage k may be refilled".  Steps entirely below the
+// diagonal and inside the matrix run a copy of the code without any predicate.
+#ifndef S3_PW
+#define S3_PW 4
+#endif
+#define S3_TR (16 * S3_PW)
+#define S3_PT (32 * S3_PW)
+#define P2_COLS 32
+#define P2_LDV 12      // row stride of the V / W operand stages ([column][8] + 4): 12 g + t are 16 distinct banks
+#define P2_LDN 10      // row stride of the V_p operand stage: 20 t + g are 16 distinct banks
+#define P2_LDC 36      // k-major column sums per warp [8][P2_LDC]
+#define P2_OPS (2 * P2_COLS * P2_LDV + P2_COLS * P2_LDN)     // doubles per operand stage
+#define P2_TILE (S3_PT * 8 * 2)                              // doubles per tile stage
+#define P2_SMEM_DOUBLES (2 * P2_OPS + 2 * P2_TILE + S3_PW * 8 * P2_LDC)
+
+template <bool FIRST, bool EVEN, bool MASKED>
+__device__ __forceinline__ void s3_issue(int k, int j0, int N, int ib0, int g, int t, int tid, const double* __restrict__ A,
+                                         const double* __restrict__ Vc, const double* __restrict__ Wc,
+                                         const double* __restrict__ Vn, double* sOps, double* sTile) {
+    double* ops = sOps + (k & 1) * P2_OPS;
+    if (tid < 4 * P2_COLS) {
+        const int col = tid >> 2, pc = tid & 3;
+        const bool in = !MASKED || j0 + col < N;
+        const size_t off = in ? ((size_t)(j0 + col) * 8 + 2 * pc) : 0;
+        cp_async16(ops + 2 * P2_COLS * P2_LDV + col * P2_LDN + 2 * pc, Vn + off, in);
+        if (!FIRST) {
+            cp_async16(ops + col * P2_LDV + 2 * pc, Vc + off, in);
+            cp_async16(ops + P2_COLS * P2_LDV + col * P2_LDV + 2 * pc, Wc + off, in);
+        }
+    }
+    double* tile = sTile + (k & 1) * P2_TILE + 2 * tid;
 #pragma unroll
     for (int rb = 0; rb < 2; ++rb) {
-        const int i = ib0 + 8 * rb + g;
-        const double* row = A + (size_t)i * N + j00 + 2 * t;
+        const int ib = ib0 + 8 * rb, i = ib + g;
+        const double* row = A + (size_t)((!MASKED || i < N) ? i : 0) * N + j0 + 2 * t;
 #pragma unroll
-        for (int cb = 0; cb < 8; ++cb) {
-            if (MASKED) {
-                const int j = j00 + 8 * cb + 2 * t;
-                c[rb][cb][0] = (i < N && j <= i) ? __ldcg(row + 8 * cb) : 0.0;
-                c[rb][cb][1] = (i < N && j + 1 <= i) ? __ldcg(row + 8 * cb + 1) : 0.0;
+        for (int cb = 0; cb < 4; ++cb) {
+            double* dst = tile + (rb * 4 + cb) * (2 * S3_PT);
+            if (!MASKED) {
+                if (EVEN) cp_async16(dst, row + 8 * cb, true);
+                else { cp_async8(dst, row + 8 * cb, true); cp_async8(dst + 1, row + 8 * cb + 1, true); }
             } else {
-                const double2 v2 = __ldcg(reinterpret_cast<const double2*>(row + 8 * cb));
-                c[rb][cb][0] = v2.x;
-                c[rb][cb][1] = v2.y;
+                const int jb = j0 + 8 * cb, j = jb + 2 * t;
+                const bool blk = i < N && jb <= ib;
+                if (EVEN) {
+                    const bool in = blk && j < N;
+                    cp_async16(dst, in ? row + 8 * cb : A, in);
+                } else {
+                    const bool in0 = blk && j < N, in1 = blk && j + 1 < N;
+                    cp_async8(dst, in0 ? row + 8 * cb : A, in0);
+                    cp_async8(dst + 1, in1 ? row + 8 * cb + 1 : A, in1);
+                }
             }
         }
     }
-    // ---- row-side operands straight from the panel arrays (each used by this warp only) ---------------------------------
-    double av[2][4], vni[2][2];
+}
+
+template <bool FIRST, bool EVEN, bool MASKED>
+__device__ __forceinline__ void s3_step(int k, int j0, int N, int ib0, int g, int t, int tid, int w, double* __restrict__ A,
+                                        const double* sOps, const double* sTile, double* sZc, const double (&av)[2][4],
+                                        const double (&vni)[2][2], double (&zi)[2][2]) {
+    const double* ops = sOps + (k & 1) * P2_OPS;
+    const double* sV = ops, *sW = ops + P2_COLS * P2_LDV, *sVn = ops + 2 * P2_COLS * P2_LDV;
+    const double* tile = sTile + (k & 1) * P2_TILE + 2 * tid;
+    double c[2][4][2];
 #pragma unroll
-    for (int rb = 0; rb < 2; ++rb) {
-        const int i = ib0 + 8 * rb + g;
-        const bool in = !MASKED || i < N;
-        if (!FIRST) {
-            av[rb][0] = in ? -__ldg(Vc + (size_t)i * 8 + t) : 0.0;
-            av[rb][1] = in ? -__ldg(Vc + (size_t)i * 8 + 4 + t) : 0.0;
-            av[rb][2] = in ? -__ldg(Wc + (size_t)i * 8 + t) : 0.0;
-            av[rb][3] = in ? -__ldg(Wc + (size_t)i * 8 + 4 + t) : 0.0;
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const double2 v2 = *reinterpret_cast<const double2*>(tile + (rb * 4 + cb) * (2 * S3_PT));
+            c[rb][cb][0] = v2.x;
+            c[rb][cb][1] = v2.y;
         }
+    // transposing shuffles: in round A the lanes of rows 0-3 publish their first element and rows 4-7 their second, in
+    // round B the other way round; a lane with even g takes (h = 0 from A, h = 1 from B), with odd g (h = 0 from B, h = 1 from A)
+    const bool lowrow = g < 4, godd = g & 1;
+    const int srcA = 4 * ((godd ? 4 : 0) + t) + (g >> 1), srcB = 4 * ((godd ? 0 : 4) + t) + (g >> 1);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ir = ib0 + 8 * rb + 4 * h + t;
-            vni[rb][h] = (!MASKED || ir < N) ? __ldg(Vn + (size_t)ir * 8 + g) : 0.0;
-        }
-    }
-    __syncthreads();   // column operands staged by the CTA are in shared memory
-    double zi[2][2];
-#pragma unroll
-    for (int rb = 0; rb < 2; ++rb) zi[rb][0] = zi[rb][1] = 0.0;
-#pragma unroll
-    for (int cb = 0; cb < 8; ++cb) {
-        const int jb = j00 + 8 * cb;
+    for (int cb = 0; cb < 4; ++cb) {
+        const int jb = j0 + 8 * cb;
         double zc0 = 0.0, zc1 = 0.0;
-        // blocks entirely above the diagonal or below row N contribute nothing (warp-uniform)
-        const double2 vnj = *reinterpret_cast<const double2*>(sVn + g * S3_LDK + 8 * cb + 2 * t);
+        const double vnj0 = sVn[(8 * cb + 2 * t) * P2_LDN + g], vnj1 = sVn[(8 * cb + 2 * t + 1) * P2_LDN + g];
         double bw0 = 0.0, bw1 = 0.0, bv0 = 0.0, bv1 = 0.0;
         if (!FIRST) {
-            bw0 = sW[t * S3_LDK + 8 * cb + g];
-            bw1 = sW[(4 + t) * S3_LDK + 8 * cb + g];
-            bv0 = sV[t * S3_LDK + 8 * cb + g];
-            bv1 = sV[(4 + t) * S3_LDK + 8 * cb + g];
+            bw0 = sW[(8 * cb + g) * P2_LDV + t];
+            bw1 = sW[(8 * cb + g) * P2_LDV + 4 + t];
+            bv0 = sV[(8 * cb + g) * P2_LDV + t];
+            bv1 = sV[(8 * cb + g) * P2_LDV + 4 + t];
         }
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb) {
             const int ib = ib0 + 8 * rb;
+            // blocks entirely above the diagonal or below row N contribute nothing (warp-uniform)
             if (!MASKED || (jb <= ib && ib < N)) {
                 const int i = ib + g, j = jb + 2 * t;
                 double u0 = c[rb][cb][0], u1 = c[rb][cb][1];
+                const bool p0 = !MASKED || (i < N && j <= i), p1 = !MASKED || (i < N && j + 1 <= i);
+                if (MASKED) {                            // pieces come whole: drop what lies above the diagonal
+                    u0 = p0 ? u0 : 0.0;
+                    u1 = p1 ? u1 : 0.0;
+                }
                 if (!FIRST) {
                     dmma_884(u0, u1, av[rb][0], bw0);
                     dmma_884(u0, u1, av[rb][1], bw1);
@@ -429,89 +464,123 @@ __device__ __forceinline__ void s3_pass_tile(double* __restrict__ A, int N, int 
                     dmma_884(u0, u1, av[rb][3], bv1);
                     double* dst = A + (size_t)i * N + j;
                     if (MASKED) {
-                        const bool p0 = i < N && j <= i, p1 = i < N && j + 1 <= i;
                         u0 = p0 ? u0 : 0.0;
                         u1 = p1 ? u1 : 0.0;
                         if (p0) __stcg(dst, u0);
                         if (p1) __stcg(dst + 1, u1);
-                    } else {
+                    } else if (EVEN) {
                         __stcg(reinterpret_cast<double2*>(dst), make_double2(u0, u1));
+                    } else {
+                        __stcg(dst, u0);
+                        __stcg(dst + 1, u1);
                     }
                 }
                 // Z[rows] += block * V_p[cols]: k = block columns, permuted (2 t | 2 t + 1) to match the C fragment
-                dmma_884(zi[rb][0], zi[rb][1], u0, vnj.x);
-                dmma_884(zi[rb][0], zi[rb][1], u1, vnj.y);
+                dmma_884(zi[rb][0], zi[rb][1], u0, vnj0);
+                dmma_884(zi[rb][0], zi[rb][1], u1, vnj1);
                 // Z[cols] += block' * V_p[rows], strictly lower part: B operand element (k = t -> row 4 h + t, n = g -> column g)
                 double l0 = u0, l1 = u1;
                 if (MASKED) {
                     l0 = (j < i) ? u0 : 0.0;
                     l1 = (j + 1 < i) ? u1 : 0.0;
                 }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int src = 4 * (4 * h + t) + (g >> 1);
-                    const double e0 = __shfl_sync(0xffffffffu, l0, src);
-                    const double e1 = __shfl_sync(0xffffffffu, l1, src);
-                    dmma_884(zc0, zc1, vni[rb][h], (g & 1) ? e1 : e0);
-                }
+                const double ra = __shfl_sync(0xffffffffu, lowrow ? l0 : l1, srcA);
+                const double rb2 = __shfl_sync(0xffffffffu, lowrow ? l1 : l0, srcB);
+                dmma_884(zc0, zc1, vni[rb][0], godd ? rb2 : ra);
+                dmma_884(zc0, zc1, vni[rb][1], godd ? ra : rb2);
             }
         }
-        *reinterpret_cast<double2*>(sZc + (w * 8 + g) * S3_LDC + 8 * cb + 2 * t) = make_double2(zc0, zc1);
-    }
-#pragma unroll
-    for (int rb = 0; rb < 2; ++rb) {
-        const int i = ib0 + 8 * rb + g;
-        if (!MASKED || i < N)
-            __stcg(reinterpret_cast<double2*>(zrow + (size_t)i * 8 + 2 * t), make_double2(zi[rb][0], zi[rb][1]));
+        *reinterpret_cast<double2*>(sZc + (w * 8 + g) * P2_LDC + 8 * cb + 2 * t) = make_double2(zc0, zc1);
     }
 }
 
-template <bool FIRST>
-__global__ void __launch_bounds__(S3_PASS_THREADS, 3)
+template <bool FIRST, bool EVEN>
+__global__ void __launch_bounds__(S3_PT, (S3_PW == 4 ? 3 : 2))
 s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restrict__ Vc_all, const double* __restrict__ Wc_all,
-               const double* __restrict__ Vn_all, double* __restrict__ Zp_all, int nslot) {
-    __shared__ __align__(16) double sV[8 * S3_LDK], sW[8 * S3_LDK], sVn[8 * S3_LDK];
-    __shared__ __align__(16) double sZc[4 * 8 * S3_LDC];
+               const double* __restrict__ Vn_all, double* __restrict__ Zp_all, int nslot, int nT) {
+    extern __shared__ __align__(16) double sm[];
+    double* sOps = sm;                          // [2][P2_OPS]: V | W | V_p
+    double* sTile = sm + 2 * P2_OPS;            // [2][8 pieces][threads][2]
+    double* sZc = sTile + 2 * P2_TILE;          // [warps][8][P2_LDC]
     const int s = blockIdx.y;
-    int I, J;
-    dm_tile_ij(blockIdx.x, I, J);
+    const int I = nT - 1 - blockIdx.x;          // long tile rows first
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     double* A = Aall + (size_t)s * N * N;
     const double* Vc = Vc_all + (size_t)s * N * 8;
     const double* Wc = Wc_all + (size_t)s * N * 8;
     const double* Vn = Vn_all + (size_t)s * N * 8;
-    double* zrow = Zp_all + ((size_t)s * nslot + J) * N * 8;
+    double* zrow = Zp_all + ((size_t)s * nslot + 0) * N * 8;
     double* zcol = Zp_all + ((size_t)s * nslot + I + 1) * N * 8;
-    const int i00 = R0 + S3_TILE * I, j00 = R0 + S3_TILE * J;
+    const int i00 = R0 + S3_TR * I;
+    const int ib0 = i00 + 16 * w;
+    const int nsteps = (S3_TR / P2_COLS) * (I + 1);
+    // steps whose 32 columns all lie below row i00, in a tile row that does not overhang N, need no predicate
+    const int nfree = (i00 + S3_TR > N) ? 0 : (S3_TR / P2_COLS) * I;
 
-    // column operands of the tile, k-major, zero beyond N
-    for (int idx = tid; idx < S3_TILE * 8; idx += S3_PASS_THREADS) {
-        const int jl = idx >> 3, k = idx & 7;
-        const bool in = j00 + jl < N;
-        sVn[k * S3_LDK + jl] = in ? __ldg(Vn + (size_t)j00 * 8 + idx) : 0.0;
-        if (!FIRST) {
-            sV[k * S3_LDK + jl] = in ? __ldg(Vc + (size_t)j00 * 8 + idx) : 0.0;
-            sW[k * S3_LDK + jl] = in ? __ldg(Wc + (size_t)j00 * 8 + idx) : 0.0;
+    auto issue = [&](int k) {
+        if (k < nsteps) {
+            const int j0 = R0 + P2_COLS * k;
+            if (k < nfree) s3_issue<FIRST, EVEN, false>(k, j0, N, ib0, g, t, tid, A, Vc, Wc, Vn, sOps, sTile);
+            else s3_issue<FIRST, EVEN, true>(k, j0, N, ib0, g, t, tid, A, Vc, Wc, Vn, sOps, sTile);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+
+    // row-side operands straight from the panel arrays (each used by this warp only, for the whole tile row)
+    double av[2][4], vni[2][2];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        const int i = ib0 + 8 * rb + g;
+        const bool in = i < N;
+        av[rb][0] = av[rb][1] = av[rb][2] = av[rb][3] = 0.0;
+        if (!FIRST && in) {
+            av[rb][0] = -__ldg(Vc + (size_t)i * 8 + t);
+            av[rb][1] = -__ldg(Vc + (size_t)i * 8 + 4 + t);
+            av[rb][2] = -__ldg(Wc + (size_t)i * 8 + t);
+            av[rb][3] = -__ldg(Wc + (size_t)i * 8 + 4 + t);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ir = ib0 + 8 * rb + 4 * h + t;
+            vni[rb][h] = ir < N ? __ldg(Vn + (size_t)ir * 8 + g) : 0.0;
         }
     }
-    const bool masked = (I == J) || (i00 + S3_TILE > N) || (N & 1);
-    if (masked) s3_pass_tile<FIRST, true>(A, N, i00, j00, Vc, Wc, Vn, zrow, sV, sW, sVn, sZc, w, lane);
-    else s3_pass_tile<FIRST, false>(A, N, i00, j00, Vc, Wc, Vn, zrow, sV, sW, sVn, sZc, w, lane);
-    __syncthreads();
-    // column sums of the 4 warps, in warp order
-    for (int idx = tid; idx < S3_TILE * 8; idx += S3_PASS_THREADS) {
-        const int jl = idx >> 3, k = idx & 7;
-        if (j00 + jl < N) {
-            double a = sZc[(0 * 8 + k) * S3_LDC + jl];
+    double zi[2][2];
 #pragma unroll
-            for (int ww = 1; ww < 4; ++ww) a += sZc[(ww * 8 + k) * S3_LDC + jl];
-            __stcg(zcol + (size_t)j00 * 8 + idx, a);
+    for (int rb = 0; rb < 2; ++rb) zi[rb][0] = zi[rb][1] = 0.0;
+
+    for (int k = 0; k < nsteps; ++k) {
+        const int j0 = R0 + P2_COLS * k;
+        cp_async_wait<1>();
+        __syncthreads();                                      // stage k & 1 has landed (own pieces and the shared operands)
+        if (k < nfree) s3_step<FIRST, EVEN, false>(k, j0, N, ib0, g, t, tid, w, A, sOps, sTile, sZc, av, vni, zi);
+        else s3_step<FIRST, EVEN, true>(k, j0, N, ib0, g, t, tid, w, A, sOps, sTile, sZc, av, vni, zi);
+        __syncthreads();                                      // column sums written; every warp is done with stage k & 1
+        issue(k + 2);
+        // column sums of the warps, in warp order -> slot I + 1, rows j0 .. j0 + 31
+        for (int idx = tid; idx < P2_COLS * 8; idx += S3_PT) {
+            const int jl = idx >> 3, kk = idx & 7;
+            if (j0 + jl < N) {
+                double a = sZc[(0 * 8 + kk) * P2_LDC + jl];
+#pragma unroll
+                for (int ww = 1; ww < S3_PW; ++ww) a += sZc[(ww * 8 + kk) * P2_LDC + jl];
+                __stcg(zcol + (size_t)j0 * 8 + idx, a);
+            }
         }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        const int i = ib0 + 8 * rb + g;
+        if (i < N) __stcg(reinterpret_cast<double2*>(zrow + (size_t)i * 8 + 2 * t), make_double2(zi[rb][0], zi[rb][1]));
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-static int s3_nslot(int N) { return (N - SBR_B + S3_TILE - 1) / S3_TILE + 1; }
+static int s3_nslot(int N) { return (N - SBR_B + S3_TR - 1) / S3_TR + 1; }
 
 // extra device bytes per matrix (wave sizing in run.cu)
 size_t sbr3_scratch_bytes(int N) { return ((size_t)(3 + s3_nslot(N)) * N * 8 + 72) * sizeof(double); }
@@ -532,10 +601,14 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         }
         return 1;
     }
+    const size_t pass_smem = (size_t)P2_SMEM_DOUBLES * sizeof(double);
     static bool attr_set = false;
-    if (!attr_set) {                     // three 32 KB CTAs per SM need more than the default carve-out
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    if (!attr_set) {                     // three 60 KB CTAs per SM
+#define S3_ATTR(F, E)                                                                                                  \
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<F, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem)); \
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<F, E>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+        S3_ATTR(true, true); S3_ATTR(true, false); S3_ATTR(false, true); S3_ATTR(false, false);
+#undef S3_ATTR
         attr_set = true;
     }
     const int nslot = s3_nslot(N);
@@ -556,7 +629,7 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         double* Vn = Vbuf[p & 1];
         if (stop_after >= 0 && launched >= stop_after) break;
 #define S3_PANEL(RPT)                                                                                                  \
-        s3_panel_kernel<RPT><<<S, S3_PANEL_WARPS * 32, 0, ctx->stream>>>(A, N, j1, tau, Vc, Wb, Vn, GT, Zp, nslot, nused)
+        s3_panel_kernel<RPT><<<S, S3_PANEL_WARPS * 32, 0, ctx->stream>>>(A, N, j1, tau, Vc, Wb, Vn, GT, Zp, nslot, nused, S3_TR)
         if (rpt <= 1) S3_PANEL(1);
         else if (rpt == 2) S3_PANEL(2);
         else if (rpt == 3) S3_PANEL(3);
@@ -567,10 +640,13 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         if (last) break;
         if (stop_after >= 0 && launched >= stop_after) break;
         const int m = N - R0;
-        const int nT = (m + S3_TILE - 1) / S3_TILE;
-        const dim3 grid(nT * (nT + 1) / 2, S);
-        if (p == 0) s3_pass_kernel<true><<<grid, S3_PASS_THREADS, 0, ctx->stream>>>(A, N, R0, Vc, Wb, Vn, Zp, nslot);
-        else s3_pass_kernel<false><<<grid, S3_PASS_THREADS, 0, ctx->stream>>>(A, N, R0, Vc, Wb, Vn, Zp, nslot);
+        const int nT = (m + S3_TR - 1) / S3_TR;
+        const dim3 grid(nT, S);
+        const bool even = (N & 1) == 0;
+#define S3_PASS(F, E) s3_pass_kernel<F, E><<<grid, S3_PT, pass_smem, ctx->stream>>>(A, N, R0, Vc, Wb, Vn, Zp, nslot, nT)
+        if (p == 0) { if (even) S3_PASS(true, true); else S3_PASS(true, false); }
+        else { if (even) S3_PASS(false, true); else S3_PASS(false, false); }
+#undef S3_PASS
         MCOSB_LAUNCHED(ctx, MK_SY2SB_PASS);
         ++launched;
         nused = nT + 1;

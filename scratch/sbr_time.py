@@ -66,4 +66,4 @@ ref = np.linalg.eigvalsh(c)
 dd, ee = d[0].cpu().numpy(), e[0].cpu().numpy()
 t = np.diag(dd) + np.diag(ee[:n - 1], 1) + np.diag(ee[:n - 1], -1)
 err = np.abs(np.linalg.eigvalsh(t) - ref).max()
-print(f"N={n} S={s} eig err {err:.2e} :: " + "  ".join(f"{k} {1e3 * ms / cnt / s:.2f} us/matrix" for k, (ms, cnt) in kt.items() if cnt))
+print(f"N={n} S={s} eig err {err:.2e} :: " + "  ".join(f"{k} {1e3 * ms / reps / s:.2f} us/matrix ({cnt // reps} launches)" for k, (ms, cnt) in kt.items() if cnt))
