@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "sbr.cuh"
 
 // X and Z of the sampling + moments stage are materialised per sub-chunk of this many bytes (each); larger chunks mean
 // fewer, longer SYRK / TRMM launches (less tail), at 2 x this much HBM
@@ -224,7 +225,7 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
         }
         const size_t free_b = ctx->mem_budget > held ? ctx->mem_budget - held : 0;
         // per simulation: cov + denoise work matrix + HRP D and E (4 N^2), inverse-iteration scratch, small vectors
-        size_t per_sim = (5 * N * N + 6 * N * 16 + 16 * N) * sizeof(double);
+        size_t per_sim = (5 * N * N + 6 * N * 16 + 16 * N) * sizeof(double) + sbr3_scratch_bytes(N);   // + panel arrays and Z partials of the band reduction
         for (int o = 0; o < nopt; ++o)
             if (plan->optimizers[o] == MCOSB_OPT_NCO) {   // NCO: cluster-block work matrix, centres when they spill to HBM
                 const size_t mk = plan->nco_max_clusters > 0 ? (size_t)plan->nco_max_clusters : N / 2;

@@ -7,7 +7,8 @@
 
 #define SBR_B 8
 #ifndef SBR_STAGE1_DEFAULT
-#define SBR_STAGE1_DEFAULT(N) ((N) <= 696 ? 1 : 2)   // which dense -> band kernel serves size N by default
+#define SBR_STAGE1_DEFAULT(N) 3   // which dense -> band kernel serves size N by default (3 = batched, sy2sb3.cu: measured
+                                  // faster than the one-CTA kernels at every N from 128 to 1024, profiles/sy2sb3_r02.md)
 #endif
 #define SBR_MIN_N 128   // below this the one-stage kernels are used (mcosb_dev_eig_prepare)
 

@@ -135,13 +135,26 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
                 // the previous pass left the row-side sum of this row in slot 0 and the column-side sums of the tile rows
                 // I >= R = (i - j1) / tr in slots I + 1 (tr = rows per tile row of the pass)
                 const double* zp = Zp_all + ((size_t)s * nslot * N + i) * 8;
-                for (int sl = (i - j1) / tr; sl < nused; ++sl) {
-                    const double2* q2 = reinterpret_cast<const double2*>(zp + (size_t)(sl == (i - j1) / tr ? 0 : sl) * N * 8);
+                // four slots in flight at a time; the additions stay in slot order
+                const int sl0 = (i - j1) / tr;
+                for (int sb = sl0; sb < nused; sb += 4) {
+                    double2 buf[4][4];
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        const double2 a = __ldcg(q2 + x);
-                        z[2 * x] += a.x;
-                        z[2 * x + 1] += a.y;
+                    for (int u = 0; u < 4; ++u) {
+                        const int sl = sb + u;
+                        const double2* q2 = reinterpret_cast<const double2*>(zp + (size_t)(sl == sl0 ? 0 : min(sl, nused - 1)) * N * 8);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) buf[u][x] = __ldcg(q2 + x);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (sb + u < nused) {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                z[2 * x] += buf[u][x].x;
+                                z[2 * x + 1] += buf[u][x].y;
+                            }
+                        }
                     }
                 }
                 const double2* vq = reinterpret_cast<const double2*>(Vc + (size_t)i * 8);

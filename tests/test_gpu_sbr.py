@@ -165,13 +165,14 @@ def test_automatic_method_outside_the_two_stage_range():
         eng.set_eig_method(3)
 
 
-@pytest.mark.parametrize("force_old", ["0", "1"])
-def test_both_stage1_kernels_over_their_size_ranges(force_old):
-    """The automatic choice uses the round-1 dense -> band kernel up to N = 696 and sy2sb2 above; MCOSB_SY2SB_OLD forces one
-    of them wherever it applies.  Both must give a band similar to the input over their whole range (two matrices per SM,
-    the cp.async ring with one and two column sub-passes, the register-ring variant above 640)."""
+@pytest.mark.parametrize("kind", ["1", "2", "3"])
+def test_all_stage1_kernels_over_their_size_ranges(kind):
+    """The automatic choice is the batched dense -> band reduction (sy2sb3.cu: panel kernel + tile pass over all matrices);
+    MCOSB_STAGE1 forces the one-CTA-per-matrix kernels of round 1 (sy2sb.cu, N <= 696) and of round 2's first session
+    (sy2sb2.cu) wherever they apply.  All must give a band similar to the input over their whole range (odd sizes take the
+    8-byte copy path of the batched pass; tile rows that overhang N and the diagonal tiles take its predicated steps)."""
     import subprocess, sys, os, textwrap
-    sizes = [10, 17, 64, 129, 255, 256, 257, 333, 440, 441, 500, 512, 513, 600, 640, 641, 696] + ([] if force_old == "1" else [777, 1000])
+    sizes = [10, 11, 17, 64, 65, 73, 129, 255, 256, 257, 333, 440, 441, 500, 512, 513, 600, 640, 641, 696] + ([] if kind == "1" else [777, 1000, 1023])
     code = textwrap.dedent(f"""
         import numpy as np
         from mcos_b200.engine import Engine
@@ -191,6 +192,6 @@ def test_both_stage1_kernels_over_their_size_ranges(force_old):
             eng.close()
         print("ok")
     """)
-    env = dict(os.environ, MCOSB_SY2SB_OLD=force_old, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, MCOSB_STAGE1=kind, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
