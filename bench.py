@@ -61,6 +61,11 @@ def kernel_models(n, t):
         "tridiag": ("fp64", 4.0 * n3 / 3, "flop"),                        # Householder tridiagonalisation
         "tridiag2": ("fp64", 4.0 * n3 / 3, "flop"),                       # blocked, lower triangle only
         "sy2sb": ("tensor", 4.0 * n3 / 3, "flop"),                        # dense -> band (b = 8): rank-16 update + A V on DMMA
+        # batched dense -> band (sy2sb3.cu): the pass reads and writes the trailing triangle once per panel of 8 columns,
+        # 2 x 8 B x sum_p m_p^2 / 2 = N^3 / 3 bytes (41.7 MB at N = 500; 6.4 us at the measured HBM peak against 4.5 us for its
+        # 4 N^3 / 3 flop on the DMMA pipe, so HBM is the binding roofline); the panel kernel moves ~6 x 64 B per row and panel
+        "sy2sb_pass": ("hbm", n3 / 3, "B"),
+        "sy2sb_panel": ("hbm", 6 * 64.0 * n * n / 16, "B"),
         "sb2st": ("fp64", 6.0 * 8 * n * n, "flop"),                       # bulge chasing, 6 N^2 b flop
         "q2back": ("hbm", 8.0 * n * n, "B"),                              # stage-2 reflectors read once per simulation
         "eigvals": ("fp64", 2.0 * 2 * 64 * n * n, "flop"),                # 64 bisection steps x N-step Sturm recurrence
@@ -472,6 +477,8 @@ def run_native(args):
             ach, peak, u = rate / 1e12, fp64["dmul_dadd_tinstr"], "Tinstr/s"
         table[name] = {"ms": round(ms, 3), "launches": cnt, "share": None, "bound": bound, "achieved": ach, "peak": peak,
                        "unit": u, "frac": ach / peak}
+        if name == "sy2sb_pass":   # the same launches against the FP64 tensor roofline (4 N^3 / 3 flop)
+            table[name]["frac_tensor"] = 4.0 * N_ASSETS ** 3 / 3 * sims_timed / (ms * 1e-3) / 1e12 / fp64["dmma_tflops"]
     tot = sum(v["ms"] for v in table.values()) or 1.0
     # launches that do next to nothing in this plan (the Ledoit-Wolf coefficient kernel: the shrink itself is folded into
     # the de-noiser's correlation pass; HRP's exact-distance kernel, which only flagged simulations enter) have no

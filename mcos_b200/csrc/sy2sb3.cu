@@ -87,15 +87,25 @@ __device__ __forceinline__ double s3_reduce8(double (&v)[8], int lane) {
 // Panel kernel.  Row i = j1 + tid + NT r of matrix s; rho = i - R0 = tid - 8 + NT r is its index below the band.
 // Vc = V_{p-1} and Zp = partial products of the previous pass (read), Wc = W_{p-1} (written), Vn = V_p (written),
 // GT = [64 strictly-upper entries of V'V | 8 tau] of the panel whose W is still to be formed (read, then replaced).
-template <int RPT>
-__global__ void __launch_bounds__(S3_PANEL_WARPS * 32, (RPT <= 2 ? 2 : 1))
+#define S3_PANEL_SMEM(NW) ((size_t)(2 * (NW) * 256 + (NW) * 64 + 3 * 64 + 8 + 2 * (NW) * 8 + 16 + 2 * 64) * sizeof(double))
+template <int RPT, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW * RPT <= 16 ? 2 : 1))
 s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ tauall, const double* __restrict__ Vc_all,
                 double* __restrict__ Wc_all, double* __restrict__ Vn_all, double* __restrict__ GT_all,
                 const double* __restrict__ Zp_all, int nslot, int nused, int tr) {
-    constexpr int NW = S3_PANEL_WARPS, NT = NW * 32;
-    __shared__ __align__(16) double stV[NW][32 * 8];
-    __shared__ __align__(16) double stY[NW][32 * 8];
-    __shared__ double partM[NW * 64], M0[64], Mm[64], Gm[64], tauS[8], red[2 * NW * 8], rowc[16], pv[64], pw[64];
+    constexpr int NT = NW * 32;
+    extern __shared__ __align__(16) double psm[];
+    double (*stV)[32 * 8] = reinterpret_cast<double (*)[32 * 8]>(psm);
+    double (*stY)[32 * 8] = reinterpret_cast<double (*)[32 * 8]>(psm + NW * 256);
+    double* partM = psm + 2 * NW * 256;
+    double* M0 = partM + NW * 64;
+    double* Mm = M0 + 64;
+    double* Gm = Mm + 64;
+    double* tauS = Gm + 64;
+    double* red = tauS + 8;
+    double* rowc = red + 2 * NW * 8;
+    double* pv = rowc + 16;
+    double* pw = pv + 64;
 
     const int s = blockIdx.x;
     double* A = Aall + (size_t)s * N * N;
@@ -116,6 +126,15 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
     for (int r = 0; r < RPT; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[r][c] = wv[r][c] = 0.0;
+    // the panel's own columns are needed only after the W phase: their loads go out first
+    double p[RPT][8];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = j1 + tid + NT * r;
+        const double* row = A + (size_t)min(i, N - 1) * N + j1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p[r][c] = __ldcg(row + min(c, ncols - 1));
+    }
 
     if (first) {
         for (int i = tid; i < N; i += NT) tau[i] = 0.0;
@@ -233,17 +252,12 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
     }
 
     // ---- panel columns j1 .. j1+7, rows j1 .. N-1: load, bring up to date with (V_{p-1}, W_{p-1}) ------------------------
-    double p[RPT][8];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const int i = j1 + tid + NT * r;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) p[r][c] = 0.0;
+        for (int c = 0; c < 8; ++c) p[r][c] = (i < N && c < ncols && j1 + c <= i) ? p[r][c] : 0.0;
         if (i < N) {
-            const double* row = A + (size_t)i * N + j1;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < ncols && j1 + c <= i) p[r][c] = __ldcg(row + c);
             if (!first) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -374,6 +388,9 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
 #ifndef S3_PW
 #define S3_PW 4
 #endif
+#ifndef S3_L2_AHEAD
+#define S3_L2_AHEAD 2      // steps of L2 prefetch ahead of the cp.async ring (0 = off)
+#endif
 #define S3_TR (16 * S3_PW)
 #define S3_PT (32 * S3_PW)
 #define P2_COLS 32
@@ -389,8 +406,8 @@ __device__ __forceinline__ void s3_issue(int k, int j0, int N, int ib0, int g, i
                                          const double* __restrict__ Vc, const double* __restrict__ Wc,
                                          const double* __restrict__ Vn, double* sOps, double* sTile) {
     double* ops = sOps + (k & 1) * P2_OPS;
-    if (tid < 4 * P2_COLS) {
-        const int col = tid >> 2, pc = tid & 3;
+    for (int q = tid; q < 4 * P2_COLS; q += S3_PT) {
+        const int col = q >> 2, pc = q & 3;
         const bool in = !MASKED || j0 + col < N;
         const size_t off = in ? ((size_t)(j0 + col) * 8 + 2 * pc) : 0;
         cp_async16(ops + 2 * P2_COLS * P2_LDV + col * P2_LDN + 2 * pc, Vn + off, in);
@@ -508,7 +525,7 @@ __device__ __forceinline__ void s3_step(int k, int j0, int N, int ib0, int g, in
 }
 
 template <bool FIRST, bool EVEN>
-__global__ void __launch_bounds__(S3_PT, (S3_PW == 4 ? 3 : 2))
+__global__ void __launch_bounds__(S3_PT, (S3_PW == 4 ? 3 : (S3_PW == 2 ? 5 : 2)))
 s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restrict__ Vc_all, const double* __restrict__ Wc_all,
                const double* __restrict__ Vn_all, double* __restrict__ Zp_all, int nslot, int nT) {
     extern __shared__ __align__(16) double sm[];
@@ -565,8 +582,22 @@ s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restric
 #pragma unroll
     for (int rb = 0; rb < 2; ++rb) zi[rb][0] = zi[rb][1] = 0.0;
 
+    // L2 prefetch of this warp's 16 x 32 piece of step k: one 128-byte half row per lane
+    auto l2_prefetch = [&](int k) {
+        const int row = ib0 + (lane >> 1), col = R0 + P2_COLS * k + 16 * (lane & 1);
+        if (k < nsteps && row < N && col + 15 <= row && col + 15 < N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A + (size_t)row * N + col));
+    };
+#if S3_L2_AHEAD > 0
+#pragma unroll
+    for (int k = 2; k < 2 + S3_L2_AHEAD; ++k) l2_prefetch(k);
+#endif
+
     for (int k = 0; k < nsteps; ++k) {
         const int j0 = R0 + P2_COLS * k;
+#if S3_L2_AHEAD > 0
+        l2_prefetch(k + 2 + S3_L2_AHEAD);                     // the cp.async of step k + 2 is issued at the end of this step
+#endif
         cp_async_wait<1>();
         __syncthreads();                                      // stage k & 1 has landed (own pieces and the shared operands)
         if (k < nfree) s3_step<FIRST, EVEN, false>(k, j0, N, ib0, g, t, tid, w, A, sOps, sTile, sZc, av, vni, zi);
@@ -622,6 +653,8 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<F, E>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
         S3_ATTR(true, true); S3_ATTR(true, false); S3_ATTR(false, true); S3_ATTR(false, false);
 #undef S3_ATTR
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_panel_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)S3_PANEL_SMEM(16)));
         attr_set = true;
     }
     const int nslot = s3_nslot(N);
@@ -633,7 +666,6 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
     double* Vbuf[2] = {Vb, Vb + (size_t)S * N * 8};
     static const int stop_after = getenv("MCOSB_S3_STOP") ? atoi(getenv("MCOSB_S3_STOP")) : -1;   // debugging: launches to run
     int launched = 0;
-    const int rpt = (N + S3_PANEL_WARPS * 32 - 1) / (S3_PANEL_WARPS * 32);
     int nused = 0;
     for (int p = 0, j1 = 0;; ++p, j1 += SBR_B) {
         const int R0 = j1 + SBR_B;
@@ -641,12 +673,11 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         double* Vc = Vbuf[(p + 1) & 1];
         double* Vn = Vbuf[p & 1];
         if (stop_after >= 0 && launched >= stop_after) break;
-#define S3_PANEL(RPT)                                                                                                  \
-        s3_panel_kernel<RPT><<<S, S3_PANEL_WARPS * 32, 0, ctx->stream>>>(A, N, j1, tau, Vc, Wb, Vn, GT, Zp, nslot, nused, S3_TR)
-        if (rpt <= 1) S3_PANEL(1);
-        else if (rpt == 2) S3_PANEL(2);
-        else if (rpt == 3) S3_PANEL(3);
-        else S3_PANEL(4);
+#define S3_PANEL(RPT, NW)                                                                                              \
+        s3_panel_kernel<RPT, NW><<<S, NW * 32, S3_PANEL_SMEM(NW), ctx->stream>>>(A, N, j1, tau, Vc, Wb, Vn, GT, Zp, nslot, nused, S3_TR)
+        if (N <= 256) S3_PANEL(1, 8);
+        else if (N <= 512) S3_PANEL(2, 8);
+        else S3_PANEL(2, 16);
 #undef S3_PANEL
         MCOSB_LAUNCHED(ctx, MK_SY2SB_PANEL);
         ++launched;
