@@ -11,7 +11,9 @@
 //                         (iterate in registers, reflector rows read coalesced), write the eigenvector;
 //   reconstruct_kernel    elementwise: cov_ij = clip((lbar d_ij + sum_s (lam_s - lbar) v_si v_sj) / sqrt(r_i r_j)) s_i s_j.
 // Simulations with more than EV3_VMAX signal eigenvalues are left to eigvec_kernel (it skips the others).
+#include <cstdlib>
 #include "common.cuh"
+#include "dmma.cuh"
 #include "sbr.cuh"
 
 #define EV3_VMAX 16
@@ -197,6 +199,227 @@ __global__ void __launch_bounds__(256) backtransform_kernel(const double* __rest
     }
 }
 
+// Compact-WY back-transformation for the panel reflectors of the band reduction (off = 8): x = Q_0 Q_1 ... Q_{P-1} y with
+// Q_p = H_0 ... H_7 = I - V T V', T^-1 = striu(V'V) + diag(1 / tau).  One CTA per simulation; a warp owns 32 rows of all 16
+// vectors as 4 x 2 FP64 tensor-core C fragments (16 doubles per thread).  A panel costs ONE reduction instead of eight and
+// three barriers instead of eight, and every flop of it is a DMMA:
+//   G  = V' [X | V]   8 x 24, k = rows: V straight from the reflector rows in A-fragment layout (the Gram part V'V uses the
+//                     same registers as both operands), X through a shared-memory transpose of the warp's fragments;
+//                     folded over the warps in warp order;
+//   G' = T G          16 threads, back-substitution with T^-1 = striu(V'V) + diag(1 / tau);
+//   X -= V G'         C fragments updated in place, V as A fragments, G' as 4 B fragments per thread.
+// Warps whose rows all lie above the panel skip it.  backtransform_kernel spent ~1600 cycles per REFLECTOR (barrier + 5-level
+// shuffle reduction of three interleaved CTAs).
+#define WY_LDX 20      // row stride of the staged X rows (20 t + g: 16 distinct banks)
+#define WY_SMEM(NW) ((size_t)((NW) * 32 * WY_LDX + (NW) * 192 + 192 + 128 + 2 * (NW) * 16) * sizeof(double))
+template <int RPT, int NW>
+__global__ void __launch_bounds__(NW * 32) backtransform_wy_kernel(const double* __restrict__ Aall,
+                                                                   const double* __restrict__ tauall,
+                                                                   const int* __restrict__ nfall, int N, int S,
+                                                                   const double* __restrict__ W, double* __restrict__ V,
+                                                                   int* __restrict__ status) {
+    extern __shared__ __align__(16) double wsm[];
+    double* stX = wsm;                                   // [NW][32][WY_LDX]
+    double* part = stX + NW * 32 * WY_LDX;               // [NW][8][24]
+    double* Gs = part + NW * 192;                        // [8][24]
+    double* Gp = Gs + 192;                               // [8][16]
+    double* red = Gp + 128;                              // [2][NW][16]
+    const size_t G = (size_t)S * EV3_VMAX;
+    const int sim = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nf = nfall[sim];
+    if (nf > EV3_VMAX || nf <= 0) return;
+    const double* A = Aall + (size_t)sim * N * N;
+    const double* tau = tauall + (size_t)sim * N;
+    const double* y = W + 4 * (size_t)N * G + (size_t)sim * EV3_VMAX;      // element (i, vec) at y[i * G + vec]
+    // x[r][rb][vb][e]: row 32 (w + NW r) + 8 rb + g, vector 8 vb + 2 t + e
+    double x[RPT][4][2][2];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+            const int i = 32 * (w + NW * r) + 8 * rb + g;
+#pragma unroll
+            for (int vb = 0; vb < 2; ++vb) {
+                const int v0 = 8 * vb + 2 * t;
+                const double2 a = *reinterpret_cast<const double2*>(y + (size_t)min(i, N - 1) * G + v0);
+                x[r][rb][vb][0] = (i < N && v0 < nf) ? a.x : 0.0;
+                x[r][rb][vb][1] = (i < N && v0 + 1 < nf) ? a.y : 0.0;
+            }
+        }
+    // ---- normalise every vector: scale by 1 / max |y|, then by 1 / ||y||; lane t of a warp's first quad ends up with the
+    // ---- values of vectors 8 vb + 2 t + e
+    {
+        double m4[2][2];
+#pragma unroll
+        for (int vb = 0; vb < 2; ++vb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double m = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb) m = fmax(m, fabs(x[r][rb][vb][e]));
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+                m4[vb][e] = m;
+            }
+        if (g == 0) {
+#pragma unroll
+            for (int vb = 0; vb < 2; ++vb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) red[w * 16 + 8 * vb + 2 * t + e] = m4[vb][e];
+        }
+        __syncthreads();
+        double pre[2][2];
+#pragma unroll
+        for (int vb = 0; vb < 2; ++vb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int v = 8 * vb + 2 * t + e;
+                double m = 0.0;
+                for (int ww = 0; ww < NW; ++ww) m = fmax(m, red[ww * 16 + v]);
+                pre[vb][e] = (v < nf) ? 1.0 / m : 0.0;
+                double q = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb) {
+                        x[r][rb][vb][e] *= pre[vb][e];
+                        q = fma(x[r][rb][vb][e], x[r][rb][vb][e], q);
+                    }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                m4[vb][e] = q;
+            }
+        if (g == 0) {
+#pragma unroll
+            for (int vb = 0; vb < 2; ++vb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) red[(NW + w) * 16 + 8 * vb + 2 * t + e] = m4[vb][e];
+        }
+        __syncthreads();
+        bool bad = false;
+#pragma unroll
+        for (int vb = 0; vb < 2; ++vb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int v = 8 * vb + 2 * t + e;
+                double q = 0.0;
+                for (int ww = 0; ww < NW; ++ww) q += red[(NW + ww) * 16 + v];
+                const double sc = (v < nf) ? 1.0 / sqrt(q) : 0.0;
+                bad |= (v < nf) && (!isfinite(sc) || !isfinite(pre[vb][e]));
+#pragma unroll
+                for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                    for (int rb = 0; rb < 4; ++rb) x[r][rb][vb][e] *= sc;
+            }
+        if (bad && status) atomicOr(&status[sim], MCOSB_ST_EIGVEC);
+    }
+    // ---- panels, last to first ------------------------------------------------------------------------------------------
+    const int npan = (N >= SBR_B + 2) ? (N - SBR_B - 2) / SBR_B + 1 : 0;
+    double* sx = stX + w * 32 * WY_LDX;
+    for (int p = npan - 1; p >= 0; --p) {
+        const int j1 = SBR_B * p, R0 = j1 + SBR_B;
+        double acc[3][2];
+#pragma unroll
+        for (int nb = 0; nb < 3; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+        double va[RPT][4][2];                              // V as A fragments of the update: row 8 rb + g, reflector 4 h + t
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int row0 = 32 * (w + NW * r);
+            if (row0 + 31 < R0 || row0 >= N) continue;     // warp-uniform: nothing of this panel in these rows
+            // reflector values: unconditional loads from clamped rows, structural zeros and ones put in afterwards
+            double vg[8];                                  // V as A = B fragments of G: row 4 q + t, reflector g
+#pragma unroll
+            for (int q = 0; q < 8; ++q) vg[q] = __ldg(A + (size_t)(j1 + g) * N + min(max(row0 + 4 * q + t, R0), N - 1));
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    va[r][rb][h] = __ldg(A + (size_t)(j1 + 4 * h + t) * N + min(max(row0 + 8 * rb + g, R0), N - 1));
+            // this warp's X fragments -> shared memory (row-major), read back with the rows on the k index
+            __syncwarp();
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int vb = 0; vb < 2; ++vb)
+                    *reinterpret_cast<double2*>(sx + (8 * rb + g) * WY_LDX + 8 * vb + 2 * t) =
+                        make_double2(x[r][rb][vb][0], x[r][rb][vb][1]);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = row0 + 4 * q + t, rho = i - R0;
+                const double a = (i >= N || rho < g) ? 0.0 : (rho == g ? 1.0 : vg[q]);
+                dmma_884(acc[0][0], acc[0][1], a, sx[(4 * q + t) * WY_LDX + g]);
+                dmma_884(acc[1][0], acc[1][1], a, sx[(4 * q + t) * WY_LDX + 8 + g]);
+                dmma_884(acc[2][0], acc[2][1], a, a);
+            }
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = row0 + 8 * rb + g, rho = i - R0, c = 4 * h + t;
+                    va[r][rb][h] = (i >= N || rho < c) ? 0.0 : (rho == c ? -1.0 : -va[r][rb][h]);
+                }
+        }
+#pragma unroll
+        for (int nb = 0; nb < 3; ++nb)
+            *reinterpret_cast<double2*>(part + w * 192 + g * 24 + 8 * nb + 2 * t) = make_double2(acc[nb][0], acc[nb][1]);
+        __syncthreads();
+        if (tid < 192) {
+            double a = part[tid];
+#pragma unroll
+            for (int ww = 1; ww < NW; ++ww) a += part[ww * 192 + tid];
+            Gs[tid] = a;
+        }
+        __syncthreads();
+        if (tid < EV3_VMAX) {                                  // T^-1 G' = G for vector tid: back-substitution
+            double gp[8];
+#pragma unroll
+            for (int c = 7; c >= 0; --c) {
+                double a = Gs[c * 24 + tid];
+#pragma unroll
+                for (int xx = c + 1; xx < 8; ++xx) a = fma(-Gs[c * 24 + EV3_VMAX + xx], gp[xx], a);
+                gp[c] = a * tau[j1 + c];
+                Gp[c * 16 + tid] = gp[c];
+            }
+        }
+        __syncthreads();
+        double bg[2][2];                                       // G' as B fragments: reflector 4 h + t, vector 8 vb + g
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int vb = 0; vb < 2; ++vb) bg[h][vb] = Gp[(4 * h + t) * 16 + 8 * vb + g];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int row0 = 32 * (w + NW * r);
+            if (row0 + 31 < R0 || row0 >= N) continue;
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int vb = 0; vb < 2; ++vb)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) dmma_884(x[r][rb][vb][0], x[r][rb][vb][1], va[r][rb][h], bg[h][vb]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+            const int i = 32 * (w + NW * r) + 8 * rb + g;
+            if (i < N) {
+#pragma unroll
+                for (int vb = 0; vb < 2; ++vb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int v = 8 * vb + 2 * t + e;
+                        if (v < nf) V[((size_t)sim * EV3_VMAX + v) * N + i] = x[r][rb][vb][e];
+                    }
+            }
+        }
+}
+
 // grid = (ceil(N / 128), S), 256 threads: the CTA stages the signal eigenvectors in shared memory once (they are re-read
 // N / 32 times per simulation instead of N / 8 from L2), each warp owns 4 output rows and a lane walks the columns, so one
 // shared-memory load of v_sj feeds 4 FMAs.  r_i = lbar + sum_s c_s v_si^2 is the diagonal of the clipped matrix.
@@ -288,12 +511,27 @@ int mcosb_launch_eigvec3(mcosb_ctx* ctx, int S, const double* A, const double* d
     MCOSB_LAUNCHED(ctx, MK_INVITER);
     const int off = Q2 ? SBR_B : 1;
     if (Q2) MCOSB_TRY(mcosb_launch_q2back(ctx, S, Q2, nf, W + 4 * n * G) == 1 ? MCOSB_OK : MCOSB_ERR_STATE);
+    static const bool wy_off = getenv("MCOSB_BACKTRANSFORM_WY") && atoi(getenv("MCOSB_BACKTRANSFORM_WY")) == 0;
+    if (Q2 && !wy_off && N >= SBR_B + 2) {
+        // panel reflectors of the band reduction: compact-WY, one CTA per simulation
+#define WY_LAUNCH(RPT, NW)                                                                                            \
+        do {                                                                                                          \
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(backtransform_wy_kernel<RPT, NW>,                                    \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WY_SMEM(NW)));      \
+            backtransform_wy_kernel<RPT, NW><<<S, NW * 32, WY_SMEM(NW), ctx->stream>>>(A, tau, nf, N, S, W, V, status); \
+        } while (0)
+        if (N <= 256) WY_LAUNCH(1, 8);
+        else if (N <= 512) WY_LAUNCH(1, 16);
+        else WY_LAUNCH(2, 16);
+#undef WY_LAUNCH
+    } else {
     const unsigned bt_grid = (unsigned)((G + 7) / 8);
     if (N <= 128) backtransform_kernel<4><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else if (N <= 256) backtransform_kernel<8><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else if (N <= 512) backtransform_kernel<16><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else if (N <= 768) backtransform_kernel<24><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
     else backtransform_kernel<32><<<bt_grid, 256, 2 * n * sizeof(double), ctx->stream>>>(A, tau, nf, N, S, W, V, status, off);
+    }
     MCOSB_LAUNCHED(ctx, MK_BACKTRANSFORM);
     const size_t smem = (2 * n + EV3_VMAX + EV3_VMAX * n) * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(reconstruct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
