@@ -388,6 +388,10 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
 #ifndef S3_PW
 #define S3_PW 4
 #endif
+#ifndef S3_G
+#define S3_G 1            // tile rows per CTA of the pass (their column sums share a slot); measured at N = 500: 2 -> panel 5.1
+                        // instead of 5.4 us but pass 12.8 instead of 11.6 us (imbalance, pipeline restarts), 4 -> 5.0 and 13.6
+#endif
 #ifndef S3_L2_AHEAD
 #define S3_L2_AHEAD 2      // steps of L2 prefetch ahead of the cp.async ring (0 = off)
 #endif
@@ -533,7 +537,7 @@ s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restric
     double* sTile = sm + 2 * P2_OPS;            // [2][8 pieces][threads][2]
     double* sZc = sTile + 2 * P2_TILE;          // [warps][8][P2_LDC]
     const int s = blockIdx.y;
-    const int I = nT - 1 - blockIdx.x;          // long tile rows first
+    const int Ig = (nT + S3_G - 1) / S3_G - 1 - blockIdx.x;     // group of S3_G consecutive tile rows, long ones first
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     double* A = Aall + (size_t)s * N * N;
@@ -541,7 +545,14 @@ s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restric
     const double* Wc = Wc_all + (size_t)s * N * 8;
     const double* Vn = Vn_all + (size_t)s * N * 8;
     double* zrow = Zp_all + ((size_t)s * nslot + 0) * N * 8;
-    double* zcol = Zp_all + ((size_t)s * nslot + I + 1) * N * 8;
+    double* zcol = Zp_all + ((size_t)s * nslot + Ig + 1) * N * 8;
+    // The tile rows of a group are walked one after the other by the same CTA, and their column sums go to ONE slot: from
+    // the second tile row on, a step adds its sums to what the same thread stored for the same columns one walk earlier
+    // (fixed order, so still reproducible) -- the panel kernel has S3_G times fewer slots to read.
+    for (int sub = 0; sub < S3_G; ++sub) {
+    const int I = S3_G * Ig + sub;
+    if (I >= nT) break;
+    const int nprev = (sub == 0) ? 0 : (S3_TR / P2_COLS) * I;   // steps whose columns the previous walk has already summed
     const int i00 = R0 + S3_TR * I;
     const int ib0 = i00 + 16 * w;
     const int nsteps = (S3_TR / P2_COLS) * (I + 1);
@@ -611,6 +622,7 @@ s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restric
                 double a = sZc[(0 * 8 + kk) * P2_LDC + jl];
 #pragma unroll
                 for (int ww = 1; ww < S3_PW; ++ww) a += sZc[(ww * 8 + kk) * P2_LDC + jl];
+                if (k < nprev) a += __ldcg(zcol + (size_t)j0 * 8 + idx);
                 __stcg(zcol + (size_t)j0 * 8 + idx, a);
             }
         }
@@ -621,10 +633,11 @@ s3_pass_kernel(double* __restrict__ Aall, int N, int R0, const double* __restric
         const int i = ib0 + 8 * rb + g;
         if (i < N) __stcg(reinterpret_cast<double2*>(zrow + (size_t)i * 8 + 2 * t), make_double2(zi[rb][0], zi[rb][1]));
     }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-static int s3_nslot(int N) { return (N - SBR_B + S3_TR - 1) / S3_TR + 1; }
+static int s3_nslot(int N) { return (N - SBR_B + S3_G * S3_TR - 1) / (S3_G * S3_TR) + 1; }
 
 // extra device bytes per matrix (wave sizing in run.cu)
 size_t sbr3_scratch_bytes(int N) { return ((size_t)(3 + s3_nslot(N)) * N * 8 + 72) * sizeof(double); }
@@ -674,7 +687,7 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         double* Vn = Vbuf[p & 1];
         if (stop_after >= 0 && launched >= stop_after) break;
 #define S3_PANEL(RPT, NW)                                                                                              \
-        s3_panel_kernel<RPT, NW><<<S, NW * 32, S3_PANEL_SMEM(NW), ctx->stream>>>(A, N, j1, tau, Vc, Wb, Vn, GT, Zp, nslot, nused, S3_TR)
+        s3_panel_kernel<RPT, NW><<<S, NW * 32, S3_PANEL_SMEM(NW), ctx->stream>>>(A, N, j1, tau, Vc, Wb, Vn, GT, Zp, nslot, nused, S3_G * S3_TR)
         if (N <= 256) S3_PANEL(1, 8);
         else if (N <= 512) S3_PANEL(2, 8);
         else S3_PANEL(2, 16);
@@ -685,7 +698,7 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         if (stop_after >= 0 && launched >= stop_after) break;
         const int m = N - R0;
         const int nT = (m + S3_TR - 1) / S3_TR;
-        const dim3 grid(nT, S);
+        const dim3 grid((nT + S3_G - 1) / S3_G, S);
         const bool even = (N & 1) == 0;
 #define S3_PASS(F, E) s3_pass_kernel<F, E><<<grid, S3_PT, pass_smem, ctx->stream>>>(A, N, R0, Vc, Wb, Vn, Zp, nslot, nT)
         if (p == 0) { if (even) S3_PASS(true, true); else S3_PASS(true, false); }
@@ -693,7 +706,7 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
 #undef S3_PASS
         MCOSB_LAUNCHED(ctx, MK_SY2SB_PASS);
         ++launched;
-        nused = nT + 1;
+        nused = (nT + S3_G - 1) / S3_G + 1;
     }
     return 1;
 }
