@@ -123,6 +123,7 @@ struct mcosb_ctx {
     int hrp_mode = 0;    // 0 fast MST + exact fallback, 1 exact distances only, 2 fast with every simulation sent to the fallback
     int* d_hrp_slow = nullptr;   // [1] simulations that took the exact fallback since the counter was last read
     int eig_method = 0;  // 0 auto, 1 one-stage Householder (tridiag / tridiag2), 2 two-stage (sy2sb + sb2st)
+    bool s3_attr_set = false;   // shared-memory attributes of the sy2sb3 kernels set on this context's device
     // per-kernel timing (mcosb_set_profiling): one event after every launch; a kernel's time is the gap to the
     // previous event on the stream
     bool profile = false;

@@ -659,8 +659,7 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
         return 1;
     }
     const size_t pass_smem = (size_t)P2_SMEM_DOUBLES * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {                     // three 60 KB CTAs per SM
+    if (!ctx->s3_attr_set) {   // per context (function attributes belong to its device): three 60 KB pass CTAs per SM
 #define S3_ATTR(F, E)                                                                                                  \
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<F, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass_smem)); \
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_pass_kernel<F, E>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
@@ -668,7 +667,7 @@ int mcosb_launch_sy2sb3(mcosb_ctx* ctx, int S, double* A, double* tau) {
 #undef S3_ATTR
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(s3_panel_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)S3_PANEL_SMEM(16)));
-        attr_set = true;
+        ctx->s3_attr_set = true;
     }
     const int nslot = s3_nslot(N);
     double *Vb, *Wb, *GT, *Zp;
