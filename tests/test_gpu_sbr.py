@@ -195,3 +195,71 @@ def test_all_stage1_kernels_over_their_size_ranges(kind):
     env = dict(os.environ, MCOSB_STAGE1=kind, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_batched_stage1_is_reproducible_and_batch_independent():
+    """sy2sb3 (panel kernel + tile pass over all matrices): the partial sums of Z have one writer per slot and are added in
+    slot order, so a matrix gives the same bits whatever else is in the batch and however often it is run."""
+    n = 200
+    a = _corr_batch(n, 4, 21)
+    eng = Engine(n, 2 * n)
+    eng.set_eig_method(2)
+    d0, e0, w0 = eng.tridiagonalize(a, want_work=True)
+    d1, e1, w1 = eng.tridiagonalize(a, want_work=True)
+    assert np.array_equal(d0, d1) and np.array_equal(e0, e1) and np.array_equal(np.tril(w0), np.tril(w1))
+    big = np.concatenate([a[2:3]] * 37 + [a[0:1]] * 3)          # other neighbours, another batch size
+    d2, e2 = eng.tridiagonalize(big)
+    assert np.array_equal(d2[0], d0[2]) and np.array_equal(e2[0], e0[2])
+    assert np.array_equal(d2[36], d0[2]) and np.array_equal(d2[39], d0[0]) and np.array_equal(e2[39], e0[0])
+
+
+def test_batched_stage1_more_matrices_than_one_grid_dimension():
+    """More than 32768 matrices in one call: the pass indexes the matrix by blockIdx.y and is launched in chunks."""
+    n, s = 12, 33000
+    rng = np.random.RandomState(5)
+    base = np.stack([np.corrcoef(rng.standard_normal((3 * n, n)), rowvar=False) for _ in range(3)])
+    a = base[np.arange(s) % 3]
+    eng = Engine(n, 2 * n)
+    eng.set_eig_method(2)
+    d, e = eng.tridiagonalize(a)
+    for i in (0, 1, 2, 32767, 32768, 32999):
+        assert_allclose(_tri_eigs(d[i], e[i]), np.linalg.eigvalsh(a[i]), rtol=0, atol=1e-12 * n)
+        assert np.array_equal(d[i], d[i % 3]) and np.array_equal(e[i], e[i % 3])
+
+
+def test_compact_wy_back_transformation_matches_the_reflectorwise_one():
+    """The signal eigenvectors through backtransform_wy_kernel (one DMMA reduction per panel of 8 reflectors) against the
+    reflector-by-reflector kernel (MCOSB_BACKTRANSFORM_WY=0), at a size per launch configuration and with the shapes of the
+    bench; both against the oracle."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, sys
+        from mcos_b200.engine import Engine
+        outs = []
+        for n, t in ((60, 150), (130, 520), (257, 600), (500, 1000), (777, 1600)):
+            rng = np.random.RandomState(n)
+            a = rng.standard_normal((n, 6)) * (np.arange(6) + 1.0)
+            cov_true = a @ a.T + np.diag(rng.uniform(0.5, 2.0, n))
+            covs = np.stack([np.cov(rng.multivariate_normal(np.zeros(n), cov_true, size=t), rowvar=False) for _ in range(2)])
+            eng = Engine(n, t)
+            eng.set_eig_method(2)
+            out, info = eng.denoise(covs, t)
+            assert (info["status"] == 0).all() and (info["n_facts"] > 0).all()
+            outs.append(out)
+            eng.close()
+        np.savez(sys.argv[1], *outs)
+        print("ok")
+    """)
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for wy in ("1", "0"):
+            path = os.path.join(tmp, f"wy{wy}.npz")
+            env = dict(os.environ, MCOSB_BACKTRANSFORM_WY=wy, PYTHONPATH=root)
+            out = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
+            assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+            with np.load(path) as z:
+                res[wy] = [z[k] for k in z.files]
+    for a, b in zip(res["1"], res["0"]):
+        assert_allclose(a, b, rtol=1e-11, atol=1e-13 * np.abs(b).max())
