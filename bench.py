@@ -47,12 +47,26 @@ def load_peaks():
     return hbm, src, fp64
 
 
-def kernel_models(n, t):
+def trmm_flops(cov, t):
+    """Flop per simulation of X = Z L' as the TRMM executes it: per set of 32 columns of X (= 32 rows of L, one warp
+    column) it visits the 16-wide k-slabs of L that hold a non-zero there (mcosb_set_truth lists them; a dense factor
+    gives the triangle T N^2, a block-diagonal truth much less)."""
+    low = np.linalg.cholesky(np.asarray(cov, dtype=np.float64))
+    n = low.shape[0]
+    slabs = 0
+    for r0 in range(0, n, 32):
+        rows = low[r0:r0 + 32]
+        slabs += sum(bool(np.any(rows[:, k0:k0 + 16] != 0.0)) for k0 in range(0, n, 16))
+    return 2.0 * t * 32 * 16 * slabs
+
+
+def kernel_models(n, t, cov=None):
     """Algorithmic work per simulation of each kernel: (bound, work per simulation, unit)."""
     n3 = float(n) ** 3
     return {
         "philox_normal": ("hbm", 8.0 * t * n, "B"),                       # writes Z once
-        "trmm": ("tensor", 2.0 * t * n * n / 2, "flop"),                  # triangular Z L'
+        # triangular Z L'; fewer when whole slabs of L are zero and skipped (not the case for the permuted block-diagonal truth)
+        "trmm": ("tensor", min(trmm_flops(cov, t), 2.0 * t * n * n / 2) if cov is not None else 2.0 * t * n * n / 2, "flop"),
         "colmean": ("hbm", 8.0 * t * n, "B"),
         "syrk": ("tensor", 2.0 * t * n * n / 2, "flop"),                  # lower triangle of Xc'Xc
         "lw_rownorm": ("hbm", 8.0 * t * n, "B"),
@@ -68,7 +82,9 @@ def kernel_models(n, t):
         "sy2sb_panel": ("hbm", 6 * 64.0 * n * n / 16, "B"),
         "sb2st": ("fp64", 6.0 * 8 * n * n, "flop"),                       # bulge chasing, 6 N^2 b flop
         "q2back": ("hbm", 8.0 * n * n, "B"),                              # stage-2 reflectors read once per simulation
-        "eigvals": ("fp64", 2.0 * 2 * 64 * n * n, "flop"),                # 64 bisection steps x N-step Sturm recurrence
+        # one multisection count (4 flop per recurrence step) + ~13 count-and-Newton evaluations (8 flop per step; the
+        # slowest lane of a warp, scratch/eig_newton_proto.py) per eigenvalue, N steps each
+        "eigvals": ("fp64", (4.0 + 13 * 8.0) * n * n, "flop"),
         "mpfit": ("fp64", 11 * 1000.0 * n * 5, "flop"),                   # ~11 objective passes x 1000 x N kernel terms x 5 flop (recurrence form)
         "eigvec": ("hbm", 3 * 8.0 * n * n, "B"),                          # reflectors read + cov written and rescaled
         "inviter": ("hbm", 8 * 5 * 8.0 * n * 10, "B"),                    # ~8 passes over 5 N-vectors for ~10 eigenvectors
@@ -457,7 +473,7 @@ def run_native(args):
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------------------
     hbm, hbm_src, fp64 = load_peaks()
-    models = kernel_models(N_ASSETS, N_OBS)
+    models = kernel_models(N_ASSETS, N_OBS, cov)
     sims_timed = spp          # the profiling pass is one step
     table = {}
     for name, (ms, cnt) in ktimes.items():

@@ -26,6 +26,8 @@ extern "C" int mcosb_create(mcosb_ctx** out, int device, int n_assets, int n_obs
     if (cudaMalloc(&ctx->d_mu, n * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&ctx->d_cov, n * n * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&ctx->d_chol, n * n * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_klist, ((n + 63) / 64) * ((n + 15) / 16) * sizeof(unsigned short)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_nk, ((n + 63) / 64 + 1) * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&ctx->d_hrp_slow, sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_hrp_slow, 0, sizeof(int)) != cudaSuccess) {
         mcosb_destroy(ctx);
         return MCOSB_ERR_CUDA;
@@ -43,6 +45,8 @@ extern "C" int mcosb_destroy(mcosb_ctx* ctx) {
     if (ctx->d_mu) cudaFree(ctx->d_mu);
     if (ctx->d_cov) cudaFree(ctx->d_cov);
     if (ctx->d_chol) cudaFree(ctx->d_chol);
+    if (ctx->d_klist) cudaFree(ctx->d_klist);
+    if (ctx->d_nk) cudaFree(ctx->d_nk);
     if (ctx->d_hrp_slow) cudaFree(ctx->d_hrp_slow);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -111,6 +115,48 @@ __global__ void __launch_bounds__(1024) chol_truth_kernel(double* __restrict__ L
     }
 }
 
+// The k-slabs of L a TRMM column tile has to visit (ctx->d_klist): one CTA per tile of 64 rows of L, one thread per slab of
+// 16 columns up to the diagonal; the non-empty ones are listed in ascending order.  Dense factors list every slab up to
+// the diagonal, which is what the TRMM walked before the list existed.
+__global__ void __launch_bounds__(128) chol_slab_list_kernel(const double* __restrict__ L, int n,
+                                                             unsigned short* __restrict__ klist, int* __restrict__ nk) {
+    __shared__ unsigned short flags[128];
+    const int J = blockIdx.x, KL = (n + 15) / 16;
+    const int kdiag = (min(n, (J + 1) * 64) + 15) / 16;   // slabs at or below the diagonal of the tile's last row
+    for (int base = 0, cnt = 0; base < kdiag; base += 128) {
+        const int kt = base + threadIdx.x;
+        unsigned short f = 0;
+        if (kt < kdiag) {
+            for (int r = 0; r < 64; ++r) {
+                const int j = J * 64 + r;
+                if (j >= n) break;
+                const double* row = L + (size_t)j * n;
+                bool nz = false;
+                for (int k = kt * 16; k < min(n, kt * 16 + 16); ++k) nz |= (row[k] != 0.0);
+                if (nz) f |= (r < 32) ? 0x4000 : 0x8000;
+            }
+        }
+        flags[threadIdx.x] = f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 128 && base + i < kdiag; ++i)
+                if (flags[i]) klist[(size_t)J * KL + cnt++] = (unsigned short)((base + i) | flags[i]);
+            if (base + 128 >= kdiag) nk[J] = cnt;
+            // half-slabs (32 rows x 16 columns) at or below the diagonal that turned out empty: any of them makes the list
+            // worth reading
+            int skipped = 0;
+            for (int i = 0; i < 128 && base + i < kdiag; ++i)
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int jlast = min(n, J * 64 + 32 * hf + 32) - 1;   // last row of the half
+                    if (jlast >= J * 64 + 32 * hf && (base + i) * 16 <= jlast && !(flags[i] & (hf ? 0x8000 : 0x4000))) ++skipped;
+                }
+            if (skipped) atomicAdd(&nk[gridDim.x], skipped);
+        }
+        // cnt lives in thread 0 only; the other threads never read it
+        __syncthreads();
+    }
+}
+
 extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* cov) {
     MCOSB_CHECK_CTX(ctx);
     if (!mu || !cov) return mcosb_fail(ctx, MCOSB_ERR_ARG, "mu/cov must not be null");
@@ -126,9 +172,15 @@ extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* c
     MCOSB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
     chol_truth_kernel<<<1, 1024, n * sizeof(double), ctx->stream>>>(ctx->d_chol, ctx->N, dflag);
     MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
-    int flag = 0;
+    const int n_tiles = (ctx->N + 63) / 64;
+    MCOSB_CUDA(ctx, cudaMemsetAsync(ctx->d_nk + n_tiles, 0, sizeof(int), ctx->stream));
+    chol_slab_list_kernel<<<n_tiles, 128, 0, ctx->stream>>>(ctx->d_chol, ctx->N, ctx->d_klist, ctx->d_nk);
+    MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
+    int flag = 0, skipped = 0;
     MCOSB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MCOSB_CUDA(ctx, cudaMemcpyAsync(&skipped, ctx->d_nk + n_tiles, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MCOSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->chol_sparse = skipped > 0;
     ctx->ideal_key.clear();  // ideal allocations belong to the previous truth
     ctx->have_truth = true;  // mu/cov are usable by the estimators even if sampling is not
     if (flag) return mcosb_fail(ctx, MCOSB_ERR_NOT_PD, "true covariance is not positive definite");

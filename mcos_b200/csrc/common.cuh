@@ -110,6 +110,12 @@ struct mcosb_ctx {
     double* d_mu = nullptr;    // true mu [N]
     double* d_cov = nullptr;   // true cov [N][N]
     double* d_chol = nullptr;  // lower Cholesky factor of the true cov [N][N]
+    // k-slabs (16 columns of L) that are not entirely zero, per tile of 64 rows of L, written by mcosb_set_truth: the TRMM
+    // walks this list instead of 0 .. diagonal (a block-diagonal truth has a block-diagonal factor).  Entry = slab index
+    // | 0x4000 if rows 0..31 of the tile have a non-zero in the slab | 0x8000 for rows 32..63.
+    unsigned short* d_klist = nullptr;   // [ceil(N / 64)][ceil(N / 16)]
+    int* d_nk = nullptr;                 // [ceil(N / 64)] entries used, then [1] the number of zero slabs found below the diagonal
+    bool chol_sparse = false;            // the list skips something: the TRMM reads it
     bool have_truth = false;
     void* slot_ptr[SL_COUNT] = {};
     size_t slot_bytes[SL_COUNT] = {};

@@ -160,10 +160,12 @@ trmm_kernel(const double* __restrict__ Z, const double* __restrict__ L, const do
 #define T2_STAGE ((DM_BM + T2_BN) * DM_LD_MMAJOR)
 // ADDMU = false writes Y = Z L' = X - mu (the fused loop: its moments are taken from the pre-centred draws, mcosb_dev_moments
 // with `shift`), which also takes the mu loads out of the epilogue.
-template <bool VEC, bool ADDMU>
+// SPARSE: walk the list of non-zero k-slabs of L (mcosb_set_truth found whole slabs of zeros below the diagonal, e.g. a
+// block-diagonal truth); otherwise every slab up to the diagonal, without the list reads.
+template <bool VEC, bool ADDMU, bool SPARSE>
 __global__ void __launch_bounds__(T2_THREADS, 2)
 trmm2_kernel(const double* __restrict__ Z, const double* __restrict__ L, const double* __restrict__ mu, size_t M, int N,
-             double* __restrict__ X) {
+             double* __restrict__ X, const unsigned short* __restrict__ klist, const int* __restrict__ nk) {
     extern __shared__ double sm[];
     const int J = blockIdx.x;
     const size_t m0 = (size_t)blockIdx.y * DM_BM;
@@ -200,22 +202,27 @@ trmm2_kernel(const double* __restrict__ Z, const double* __restrict__ L, const d
             else cp_async8(&Bt[row * DM_LD_MMAJOR + lk], L + (bok ? (size_t)j * N + k : 0), bok);
         }
     };
-    const int kend = min(N, (J + 1) * T2_BN);  // L[j][k] = 0 for k > j
-    const int nkt = (kend + DM_BK - 1) / DM_BK;
+    // SPARSE: the k-slabs of L with a non-zero in this tile's 64 rows, each with a bit per half of 32 rows = per warp
+    // column set.  Dense: L[j][k] = 0 for k > j only.
+    const unsigned short* kl = klist + (size_t)J * ((N + DM_BK - 1) / DM_BK);
+    const int nkt = SPARSE ? nk[J] : (min(N, (J + 1) * T2_BN) + DM_BK - 1) / DM_BK;
+    const unsigned mine = (wid & 1) ? 0x8000u : 0x4000u;
+    auto slab = [&](int it) { return SPARSE ? (int)(kl[it] & 0x3fff) : it; };
 #pragma unroll
     for (int st = 0; st < DM_STAGES - 1; ++st) {
-        if (st < nkt) issue(st, st);
+        if (st < nkt) issue(slab(st), st);
         cp_async_commit();
     }
-    for (int kt = 0; kt < nkt; ++kt) {
+    for (int it = 0; it < nkt; ++it) {
         cp_async_wait<DM_STAGES - 2>();
         __syncthreads();
-        const double* At = sm + (size_t)(kt % DM_STAGES) * T2_STAGE;
+        const double* At = sm + (size_t)(it % DM_STAGES) * T2_STAGE;
         auto next = [&] {
-            if (kt + DM_STAGES - 1 < nkt) issue(kt + DM_STAGES - 1, (kt + DM_STAGES - 1) % DM_STAGES);
+            if (it + DM_STAGES - 1 < nkt) issue(slab(it + DM_STAGES - 1), (it + DM_STAGES - 1) % DM_STAGES);
             cp_async_commit();
         };
-        if (kt * DM_BK <= J * T2_BN + wn0 + DM_WN - 1)   // L[j][k] = 0 for k > j: nothing for this warp's columns
+        // otherwise the slab holds only zeros for this warp's columns
+        if (SPARSE ? (kl[it] & mine) != 0 : it * DM_BK <= J * T2_BN + wn0 + DM_WN - 1)
             dmma_slab<false, false, false>(At, At + DM_TILE_MMAJOR, wm0, wn0, lane, acc, next);
         else
             next();
@@ -267,15 +274,22 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool a
     } else {
         const size_t smem = (size_t)DM_STAGES * T2_STAGE * sizeof(double);
         dim3 g((N + T2_BN - 1) / T2_BN, (unsigned)row_tiles);
-#define T2_LAUNCH(V, A)                                                                                               \
+#define T2_LAUNCH(V, A, SP)                                                                                           \
     do {                                                                                                              \
-        MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<V, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        trmm2_kernel<V, A><<<g, T2_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);                \
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<V, A, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        trmm2_kernel<V, A, SP><<<g, T2_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX, ctx->d_klist, \
+                                                                     ctx->d_nk);                                      \
     } while (0)
-        if (vec && add_mu) T2_LAUNCH(true, true);
-        else if (vec) T2_LAUNCH(true, false);
-        else if (add_mu) T2_LAUNCH(false, true);
-        else T2_LAUNCH(false, false);
+#define T2_LAUNCH2(V, A)                                                                                              \
+    do {                                                                                                              \
+        if (ctx->chol_sparse) T2_LAUNCH(V, A, true);                                                                  \
+        else T2_LAUNCH(V, A, false);                                                                                  \
+    } while (0)
+        if (vec && add_mu) T2_LAUNCH2(true, true);
+        else if (vec) T2_LAUNCH2(true, false);
+        else if (add_mu) T2_LAUNCH2(false, true);
+        else T2_LAUNCH2(false, false);
+#undef T2_LAUNCH2
 #undef T2_LAUNCH
     }
     MCOSB_LAUNCHED(ctx, MK_TRMM);

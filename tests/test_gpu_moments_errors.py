@@ -128,6 +128,30 @@ def test_sampler_matches_spec(stock, n, t):
     assert np.array_equal(x2, x[1:])
 
 
+@pytest.mark.parametrize("n,blocks,t", [(500, 10, 24), (200, 4, 40), (130, 13, 17), (96, 1, 20)])
+def test_sampler_sparse_cholesky_factor(n, blocks, t):
+    """The TRMM visits only the 16-column slabs of L that hold a non-zero for its 64 rows (mcosb_set_truth lists them):
+    block-diagonal truths -- the BASELINE configurations -- skip most of the triangle.  The draws must still be
+    mu + Z L' for the spec's Z; an arrow-shaped truth (dense last rows, diagonal elsewhere) and a permuted
+    block structure exercise slab lists that are not contiguous."""
+    mu, cov = block_diagonal_truth(n, n_blocks=blocks)
+    rng = np.random.RandomState(n)
+    cases = [(mu, cov)]
+    arrow = np.diag(rng.uniform(0.5, 1.5, n))
+    arrow[:, -3:] = arrow[-3:, :] = 0.02
+    arrow[np.arange(n), np.arange(n)] = rng.uniform(1.0, 2.0, n)
+    cases.append((mu, arrow))
+    perm = rng.permutation(n)
+    cases.append((mu[perm], cov[np.ix_(perm, perm)]))
+    for m, c in cases:
+        eng = Engine(n, t, seed=99)
+        eng.set_truth(m, c)
+        x = eng.sample(2, sim_id0=3)
+        z = standard_normals([3, 4], t, n, 99)
+        want = m + z @ np.linalg.cholesky(c).T
+        assert_allclose(x, want, rtol=1e-11, atol=1e-12 * np.abs(want).max())
+
+
 def test_sampler_distribution():
     """Sample mean / covariance of many draws converge to the truth (distributional check of the GPU RNG)."""
     mu, cov = block_diagonal_truth(20, n_blocks=2)
