@@ -85,7 +85,9 @@ def kernel_models(n, t, cov=None):
         # one multisection count (4 flop per recurrence step) + ~13 count-and-Newton evaluations (8 flop per step; the
         # slowest lane of a warp, scratch/eig_newton_proto.py) per eigenvalue, N steps each
         "eigvals": ("fp64", (4.0 + 13 * 8.0) * n * n, "flop"),
-        "mpfit": ("fp64", 11 * 1000.0 * n * 5, "flop"),                   # ~11 objective passes x 1000 x N kernel terms x 5 flop (recurrence form)
+        # Taylor table of the kernel sum: 48 nodes x N x (exp ~25 + 13 x 4 flop) once, then ~11 objective passes x 1000 points
+        # x (2 Horner recurrences of degree 12 + the MP density ~40 flop)
+        "mpfit": ("fp64", 48.0 * n * 77 + 11 * 1000.0 * 92, "flop"),
         "eigvec": ("hbm", 3 * 8.0 * n * n, "B"),                          # reflectors read + cov written and rescaled
         "inviter": ("hbm", 8 * 5 * 8.0 * n * 10, "B"),                    # ~8 passes over 5 N-vectors for ~10 eigenvectors
         "backtransform": ("hbm", 8.0 * n * n / 2, "B"),                   # reflectors read once (shared by the vectors via L1/L2)

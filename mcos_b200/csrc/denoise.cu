@@ -486,7 +486,65 @@ struct MPCtx {
     int N;
     double q, inv2h2, invh2, cnorm;
     double* red;
+    // Taylor table of the kernel sum (mp_build_nodes); nodes = 0: evaluate the sum directly
+    const double* coef = nullptr;   // shared memory, [nodes][MP_DEG + 1]
+    int nodes = 0;
+    double h = 0.0, inv_delta = 0.0, delta = 0.0;
 };
+
+// The kernel sum S(x) = sum_i exp(-(x - lam_i)^2 / 2h^2) does not depend on the variance being fitted -- only the grid on which
+// the objective samples it does, and every grid lies in (0, (1 + sqrt(1/q))^2).  So S is tabulated ONCE per matrix as Taylor
+// expansions about nodes x_g = g h / 4 covering that range:
+//     S(x_g + t h) = sum_m C[g][m] t^m,   C[g][m] = sum_i c_m(u_i) exp(-u_i^2 / 2),   u_i = (x_g - lam_i) / h,
+//     c_0 = 1, c_1 = -u, c_{m+1} = (-u c_m - c_{m-1}) / (m + 1)     ((-1)^m He_m(u) / m!, probabilists' Hermite)
+// and every objective evaluation reads S and S' = -(1/h^2) sum_i E_i (x - lam_i) off the nearest node (|t| <= 1/8) with two
+// Horner recurrences of degree 12 -- truncation below 1e-16 of max S (scratch/kde_taylor_proto.py) -- instead of summing
+// N kernel terms per grid point.  Cost: one exp + ~40 FP64 instructions per (node, eigenvalue) once (48 nodes at
+// h = 0.25, q = 2), then ~30 per grid point and evaluation; the direct form costs ~4 N per grid point and evaluation.
+#define MP_DEG 12
+#define MP_NODE_DIV 4        // nodes per bandwidth
+#define MP_MAX_NODES 256     // more (a bandwidth below ~0.05 at q = 2): direct evaluation
+
+__host__ __device__ inline int mp_node_count(double q, double bandwidth) {
+    const double sq = sqrt(1.0 / q);
+    const double top = (1.0 + sq) * (1.0 + sq);
+    const double cnt = floor(top * MP_NODE_DIV / bandwidth) + 2.0;
+    return (cnt >= 2.0 && cnt <= (double)MP_MAX_NODES) ? (int)cnt : 0;
+}
+
+// All MP_THREADS threads.  One warp per node and pass, lanes over the eigenvalues, fixed summation order.
+__device__ void mp_build_nodes(const MPCtx& c, double* coef) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double invh = 1.0 / c.h;
+    for (int g = wid; g < c.nodes; g += MP_THREADS / 32) {
+        const double xg = (double)g * c.delta;
+        double acc[MP_DEG + 1];
+#pragma unroll
+        for (int m = 0; m <= MP_DEG; ++m) acc[m] = 0.0;
+        for (int i = lane; i < c.N; i += 32) {
+            const double u = (xg - c.lam[i]) * invh;
+            const double hu2 = 0.5 * u * u;
+            if (hu2 > 745.0) continue;          // exp underflows to zero
+            const double E = exp(-hu2);
+            double cm1 = 0.0, cm = E;           // c_m(u) E
+#pragma unroll
+            for (int m = 0; m <= MP_DEG; ++m) {
+                acc[m] += cm;
+                const double nx = (-u * cm - cm1) * (1.0 / (double)(m + 1));
+                cm1 = cm;
+                cm = nx;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m <= MP_DEG; ++m) {
+            double v = acc[m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) coef[g * (MP_DEG + 1) + m] = v;
+        }
+    }
+    __syncthreads();
+}
 
 // Objective and analytic derivative at v.  The Gaussian kernel sums over a UNIFORM grid obey a two-multiply recurrence:
 //   g_k = exp(-(x_k - lam)^2 / 2h^2),  g_{k+1} = g_k r_k,  r_{k+1} = r_k c,  c = exp(-dx^2 / h^2),
@@ -502,7 +560,30 @@ __device__ void mp_eval(const MPCtx& c, double v, double& f, double& g) {
     const int kb = threadIdx.x / MP_IG, ig = threadIdx.x % MP_IG;
     const int k0 = kb * MP_KB;
     double fs = 0.0, gs = 0.0;
-    {   // all 512 threads run the loop (the shuffles need full warps); the last group's points are past the grid
+    if (c.nodes > 0) {
+        for (int k = threadIdx.x; k < MP_PTS; k += MP_THREADS) {
+            // numpy.linspace: arange * step + start (two roundings, no FMA), last point forced to the stop value
+            const double x = (k == MP_PTS - 1) ? hi : __dadd_rn(__dmul_rn((double)k, step), lo);
+            int g = (int)rint(x * c.inv_delta);
+            g = min(max(g, 0), c.nodes - 1);
+            const double t = (x - (double)g * c.delta) / c.h;
+            const double* cg = c.coef + g * (MP_DEG + 1);
+            double s0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int m = MP_DEG; m >= 0; --m) {
+                d1 = fma(d1, t, s0);
+                s0 = fma(s0, t, cg[m]);
+            }
+            const double kd = -c.h * d1;                                  // sum_i E_i (x - lam_i)
+            const double rad = fmax((hi - x) * (x - lo), 0.0);
+            const double pdf = c.q / (2.0 * M_PI * v * x) * sqrt(rad);
+            const double kde = c.cnorm * s0;
+            const double dkde = -c.cnorm * kd * c.invh2 * (x / v);
+            const double r = kde - pdf;
+            fs = fma(r, r, fs);
+            gs = fma(2.0 * r, dkde + pdf / v, gs);
+        }
+    } else {   // all threads run the loop (the shuffles need full warps); the last group's points are past the grid
         double s0[MP_KB], sl[MP_KB];
 #pragma unroll
         for (int j = 0; j < MP_KB; ++j) s0[j] = sl[j] = 0.0;
@@ -736,7 +817,8 @@ __device__ bool mp_lbfgsb(const MPCtx& c, double& xout) {
 
 __global__ void __launch_bounds__(MP_THREADS) mpfit_kernel(const double* __restrict__ lamall, int N, double q,
                                                            double bandwidth, double* __restrict__ var_out,
-                                                           int* __restrict__ nf_out, int* __restrict__ status) {
+                                                           int* __restrict__ nf_out, int* __restrict__ status,
+                                                           int use_nodes) {
     extern __shared__ double sm[];
     __shared__ double red[32];
     __shared__ int s_cnt;
@@ -754,6 +836,12 @@ __global__ void __launch_bounds__(MP_THREADS) mpfit_kernel(const double* __restr
     c.inv2h2 = 1.0 / (2.0 * bandwidth * bandwidth);
     c.invh2 = 1.0 / (bandwidth * bandwidth);
     c.cnorm = 1.0 / (N * bandwidth * sqrt(2.0 * M_PI));
+    c.h = bandwidth;
+    c.delta = bandwidth / MP_NODE_DIV;
+    c.inv_delta = MP_NODE_DIV / bandwidth;
+    c.nodes = use_nodes ? mp_node_count(q, bandwidth) : 0;
+    c.coef = sm + N;
+    if (c.nodes > 0 && !any_bad) mp_build_nodes(c, sm + N);
     double v = 1.0;
     bool ok = false;
     if (!any_bad) ok = mp_lbfgsb(c, v);
@@ -1074,9 +1162,11 @@ int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double ban
     MCOSB_TRY(mcosb_dev_eig_prepare(ctx, S, dcov, A, sigma, d, e, tau, lam, &Q2, lwcoef));
 
     const double q = (double)n_obs / (double)N;
-    size_t smem_mp = n * sizeof(double);
+    static const bool mp_direct = std::getenv("MCOSB_MPFIT_DIRECT") != nullptr;   // A/B runs: sum the kernel terms per grid point
+    const int mp_nodes = mp_direct ? 0 : mp_node_count(q, bandwidth);
+    size_t smem_mp = (n + (size_t)mp_nodes * (MP_DEG + 1)) * sizeof(double);
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(mpfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mp));
-    mpfit_kernel<<<S, MP_THREADS, smem_mp, ctx->stream>>>(lam, N, q, bandwidth, dvar, nf, dstatus);
+    mpfit_kernel<<<S, MP_THREADS, smem_mp, ctx->stream>>>(lam, N, q, bandwidth, dvar, nf, dstatus, mp_nodes > 0);
     MCOSB_LAUNCHED(ctx, MK_MPFIT);
 
     // wide path (eigvec3.cu) for simulations with at most 16 signal eigenvalues; eigvec_kernel takes the others
