@@ -22,6 +22,9 @@
 #ifndef HD_ROWS
 #define HD_ROWS 32   // rows per CTA (a multiple of 8)
 #endif
+#ifndef HD_UNROLL
+#define HD_UNROLL 8  // independent row loads per lane
+#endif
 // grid = (ceil(N / HD_ROWS), S), HD_ROWS / 8 rows per warp; the square roots of the diagonal are taken once per CTA.
 // (1 - r) / 2 is an exact halving, so the multiplication by 0.5 rounds like numpy's division.
 __global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict__ cov, int N, double* __restrict__ D,
@@ -38,13 +41,27 @@ __global__ void __launch_bounds__(256) hrp_dist_kernel(const double* __restrict_
         if (row >= N) return;
         const double si = sg[row];
         double nrm = 0.0;
-        for (int j = lane; j < N; j += 32) {
-            double r = __ddiv_rn(c[(size_t)row * N + j], __dmul_rn(si, sg[j]));
-            r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-            double v = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
-            v = (j == row) ? 0.0 : v;
-            d[(size_t)row * N + j] = v;
-            nrm = fma(v, v, nrm);
+        // 8 independent loads per lane ahead of the divisions / square roots (memory-level parallelism); the additions into
+        // nrm keep their column order
+        for (int j0 = lane; j0 < N; j0 += 32 * HD_UNROLL) {
+            double x[HD_UNROLL];
+#pragma unroll
+            for (int u = 0; u < HD_UNROLL; ++u) {
+                const int j = j0 + 32 * u;
+                x[u] = (j < N) ? c[(size_t)row * N + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < HD_UNROLL; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < N) {
+                    double r = __ddiv_rn(x[u], __dmul_rn(si, sg[j]));
+                    r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+                    double v = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
+                    v = (j == row) ? 0.0 : v;
+                    d[(size_t)row * N + j] = v;
+                    nrm = fma(v, v, nrm);
+                }
+            }
         }
         if (rn) {                       // squared row norms for the Gram form of the distances (fast path)
             nrm = warp_sum(nrm);

@@ -74,6 +74,41 @@ def test_denoise_identity_and_constant_inputs():
         assert_allclose(out[i], d["cov"], rtol=1e-6, atol=1e-12)
 
 
+@pytest.mark.parametrize("n", [40, 200, 500])
+def test_eigenvalues_on_clustered_and_graded_spectra(n):
+    """The eigenvalue kernel brackets by Sturm counts and finishes with Newton steps once a bracket isolates one eigenvalue;
+    clusters never isolate and stay on bisection.  Spectra with exact multiplicities, pairs 1e-9 and 1e-13 apart, a geometric
+    grading over 10 decades and the sample correlation of the block truth must all come back within a few ulp of the
+    spectrum's scale, in descending order."""
+    rng = np.random.RandomState(n)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    spectra = []
+    lam = np.ones(n); lam[: n // 4] = 3.0; lam[n // 4: n // 2] = 0.25                     # three exact clusters
+    spectra.append(lam)
+    lam = np.linspace(0.1, 2.0, n); lam[1::2] = lam[0::2][: len(lam[1::2])] + 1e-9         # close pairs
+    lam[5] = lam[4] + 1e-13
+    spectra.append(lam)
+    spectra.append(np.geomspace(1e-10, 10.0, n))                                            # graded
+    mats = []
+    for lam in spectra:
+        a = (q * lam) @ q.T
+        a = 0.5 * (a + a.T)
+        dg = np.sqrt(np.diag(a))
+        mats.append(a / np.outer(dg, dg))         # unit diagonal: the kernel sees exactly this matrix as its correlation
+    mu, cov = block_diagonal_truth(n)
+    mats.append(np.corrcoef(rng.multivariate_normal(mu, cov, size=2 * n), rowvar=False))
+    mats = np.stack(mats)
+    eng = Engine(n, 2 * n)
+    for method in (1, 2) if n >= 128 else (1,):
+        eng.set_eig_method(method)
+        _, info = eng.denoise(mats, 2 * n)
+        for i in range(mats.shape[0]):
+            ref = np.linalg.eigvalsh(mats[i])[::-1]
+            got = info["eigvals"][i]
+            assert np.all(np.diff(got) <= 0)
+            assert_allclose(got, ref, rtol=0, atol=4e-14 * n * max(1.0, abs(ref[0])))
+
+
 def test_denoise_many_signal_eigenvalues_and_mixed_batch():
     """More than 16 signal eigenvalues takes the one-CTA-per-matrix eigenvector kernel, fewer the wide kernels; a batch
     that mixes both must give every simulation the right answer."""
