@@ -362,6 +362,8 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.sims_per_step <= 0:
+        args.sims_per_step = 48 * torch.cuda.get_device_properties(local).multi_processor_count
     spp = args.sims_per_step
     mu, cov = block_diagonal_truth(N_ASSETS)
     sim = mb.MuCovLedoitWolfObservationSimulator(mu, cov, N_OBS, seed=args.seed, device=local)
@@ -561,7 +563,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--sims-per-step", type=int, default=8192)
+    ap.add_argument("--sims-per-step", type=int, default=0,
+                    help="simulations per GPU and step; default 48 x SM count (7104 on B200): one wave of the fused loop, a "
+                         "whole number of CTA rounds for every kernel that runs 1, 2, 3, 4, 6, 8 or 16 simulations per SM")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

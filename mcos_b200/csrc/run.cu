@@ -66,6 +66,7 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, const RunPlan& rp, ui
     // ---- sampling + moments in sub-chunks so X (8TN bytes per simulation) stays small ---------------------------------
     const size_t chunk_bytes = RUN_CHUNK_BYTES;
     int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)W, chunk_bytes / (T * N * sizeof(double))));
+    CH = (W + (W + CH - 1) / CH - 1) / ((W + CH - 1) / CH);   // the same number of sub-chunks, equal sizes
     double* dX;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * T * N, &dX));
     // Ledoit-Wolf followed by the de-noiser: the shrink (one read-modify-write of every covariance matrix) is folded
@@ -238,6 +239,13 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
         wave = (int)std::max<size_t>(1, std::min<size_t>(w, 8192));
     }
     wave = std::min(wave, S);
+    if (plan->wave <= 0 && S > wave) {
+        // equal waves instead of full ones and a short remainder (every kernel of a short wave ends on a mostly idle GPU):
+        // the simulations divided over the same number of waves, rounded up to whole CTAs-per-SM rounds
+        const int nw = (S + wave - 1) / wave;
+        const int even = (S + nw - 1) / nw;
+        wave = std::min(wave, (even + ctx->num_sms - 1) / ctx->num_sms * ctx->num_sms);
+    }
 
     const double t_mem = now();
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> marks;
