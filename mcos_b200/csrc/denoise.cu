@@ -447,20 +447,47 @@ __global__ void __launch_bounds__(EV_THREADS) eigvals_kernel(const double* __res
     __syncthreads();
     // below ~4 ulp of the spectrum's scale the tridiagonal form itself is not accurate; stop there
     const double tol = 8.9e-16 * fmax(span, 1e-300);
-    for (int j = tid; j < N; j += EV_THREADS) {  // j-th smallest eigenvalue
+    // second multisection step, inside the cells: the m eigenvalues that share a cell (the bulk of a Marcenko-Pastur spectrum
+    // puts ~9 into a cell of width span / N) probe m evenly spaced interior points, one each, and every one of them takes the
+    // tightest bracket the m probes allow -- one cheap count instead of ~log2(m) Newton-capable evaluations each
+    double* xs2 = reinterpret_cast<double*>(cnts + N + (N & 1));   // [N] probe of eigenvalue j
+    int* cs2 = reinterpret_cast<int*>(xs2 + N);                    // [N] its count
+    for (int j = tid; j < N; j += EV_THREADS) {
         int l0 = 0, l1 = N - 1;                  // smallest i with cnts[i] > j (cnts[N-1] = N)
         while (l0 < l1) {
             const int mid = (l0 + l1) >> 1;
             if (cnts[mid] > j) l1 = mid; else l0 = mid + 1;
         }
+        const int ca = l0 > 0 ? cnts[l0 - 1] : 0, m = cnts[l0] - ca;
+        const double a = fma(h, (double)l0, lo);
+        const double x = fma(h * ((double)(j - ca) + 0.5), 1.0 / (double)m, a);
+        xs2[j] = x;
+        cs2[j] = (m > 1) ? sturm_count(sde, N, x) : -1;
+    }
+    __syncthreads();
+    for (int j = tid; j < N; j += EV_THREADS) {  // j-th smallest eigenvalue
+        int l0 = 0, l1 = N - 1;
+        while (l0 < l1) {
+            const int mid = (l0 + l1) >> 1;
+            if (cnts[mid] > j) l1 = mid; else l0 = mid + 1;
+        }
         double a = fma(h, (double)l0, lo), b = fma(h, (double)(l0 + 1), lo);
+        int ca = l0 > 0 ? cnts[l0 - 1] : 0, cb = cnts[l0];
+        if (cb - ca > 1) {
+            const int c0 = ca, c1 = cb;          // the cell's eigenvalues are c0 .. c1 - 1; their probes ascend with the index
+            for (int jj = c0; jj < c1; ++jj) {
+                const double x = xs2[jj];
+                const int c = cs2[jj];
+                if (c > j) { if (x < b) { b = x; cb = c; } }
+                else if (x > a) { a = x; ca = c; }
+            }
+        }
         // Bisection on the count until the bracket isolates eigenvalue j (counts j and j + 1 at its ends), then Newton on
         // p_N from the last point evaluated, kept only while it stays inside the bracket and at least halves the step;
         // the count of every evaluation still tightens the bracket, so a rejected step costs nothing.  Newton's iterate is
         // accepted once its correction is below 32 tol, or once the observed quadratic contraction |dx_k| / dx_{k-1}^2
         // puts the next error below tol / 10.  Clustered eigenvalues never isolate and stay on bisection.
         // (scratch/eig_newton_proto.py: ~10 evaluations per eigenvalue instead of 43 at N = 500.)
-        int ca = l0 > 0 ? cnts[l0 - 1] : 0, cb = cnts[l0];
         double x = 0.5 * (a + b), dxp = b - a, lam = x;
         bool nw = false;
         for (int it = 0; it < 200; ++it) {
@@ -1118,7 +1145,7 @@ int mcosb_dev_eig_prepare(mcosb_ctx* ctx, int S, const double* dcov, double* A, 
     corr_kernel<<<dim3((N + CORR_ROWS - 1) / CORR_ROWS, S), 256, n * sizeof(double), ctx->stream>>>(dcov, N, A, sigma, lwcoef);
     MCOSB_LAUNCHED(ctx, MK_CORR);
     MCOSB_TRY(mcosb_dev_tridiagonalize(ctx, S, A, d, e, tau, q2));
-    size_t smem_ev = 2 * n * sizeof(double) + n * sizeof(int);
+    size_t smem_ev = 2 * n * sizeof(double) + (n + 1) * sizeof(int) + n * (sizeof(double) + sizeof(int));   // (d, e^2), grid counts, probes
     MCOSB_CUDA(ctx, cudaFuncSetAttribute(eigvals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ev));
     eigvals_kernel<<<S, EV_THREADS, smem_ev, ctx->stream>>>(d, e, N, lam);
     MCOSB_LAUNCHED(ctx, MK_EIGVALS);

@@ -34,6 +34,9 @@
 #include <algorithm>
 
 #define S3_PANEL_WARPS 8
+#ifndef S3_PANEL_PREFETCH
+#define S3_PANEL_PREFETCH 1
+#endif
 
 __device__ __forceinline__ double s3_rcp(double x) {
     double r;
@@ -144,11 +147,37 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
         if (tid < 8) tauS[tid] = GT[64 + tid];
         __syncthreads();
         double m0 = 0.0, m1 = 0.0;
+#if S3_PANEL_PREFETCH
+        // the slots of the row are summed four at a time (register budget), i.e. in up to three dependent DRAM round trips:
+        // ask L2 for all of them now, so that the later batches are L2 hits
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = j1 + tid + NT * r;
+            if (i < N) {
+                const double* zp = Zp_all + ((size_t)s * nslot * N + i) * 8;
+                const int sl0 = (i - j1) / tr;
+                for (int sl = sl0 + 4; sl < nused; ++sl) {
+                    const double* q = zp + (size_t)sl * N * 8;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 4));
+                }
+            }
+        }
+#endif
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int i = j1 + tid + NT * r;
             if (i < N) {
                 double z[8];
+                {   // V_{p-1} row: independent of the slot sums, issued ahead of them
+                    const double2* vq = reinterpret_cast<const double2*>(Vc + (size_t)i * 8);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const double2 a = __ldcg(vq + x);
+                        v[r][2 * x] = a.x;
+                        v[r][2 * x + 1] = a.y;
+                    }
+                }
 #pragma unroll
                 for (int x = 0; x < 8; ++x) z[x] = 0.0;
                 // the previous pass left the row-side sum of this row in slot 0 and the column-side sums of the tile rows
@@ -175,13 +204,6 @@ s3_panel_kernel(double* __restrict__ Aall, int N, int j1, double* __restrict__ t
                             }
                         }
                     }
-                }
-                const double2* vq = reinterpret_cast<const double2*>(Vc + (size_t)i * 8);
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    const double2 a = __ldcg(vq + x);
-                    v[r][2 * x] = a.x;
-                    v[r][2 * x + 1] = a.y;
                 }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {       // Y U = Z

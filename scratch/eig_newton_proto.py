@@ -27,11 +27,20 @@ def solve(d, e, mode):
     h = (hi - lo) / n
     cnts = np.array([sturm(d, e2, lo + h * i)[0] for i in range(n + 1)])
     tol = 8.9e-16 * span
-    lam = np.empty(n); nev = np.zeros(n, int)
+    lam = np.empty(n); nev = np.zeros(n, int); cheap = np.zeros(n, int); probes = {}
     for j in range(n):
         l0 = int(np.searchsorted(cnts, j, side='right'))
         a, b = lo + h * (l0 - 1), lo + h * l0
         ca, cb = cnts[l0 - 1], cnts[l0]
+        if mode and cb - ca > 1:      # second multisection step: the cell's m eigenvalues probe m interior points (count only)
+            c0, c1 = ca, cb
+            if (l0, 'p') not in probes:
+                probes[(l0, 'p')] = [(a + h * (r + 0.5) / (c1 - c0), sturm(d, e2, a + h * (r + 0.5) / (c1 - c0))[0]) for r in range(c1 - c0)]
+            cheap[j] += 1
+            for xx, cc in probes[(l0, 'p')]:
+                if cc > j:
+                    if xx < b: b, cb = xx, cc
+                elif xx > a: a, ca = xx, cc
         x = 0.5 * (a + b); dxp = b - a; nw = False
         while True:
             c, p, dp = sturm(d, e2, x); nev[j] += 1
