@@ -526,7 +526,21 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
             if ((N & 1) == 0) {                 // rows are 16-byte aligned: half the load instructions (each touches 32 lines)
                 const double2* pa = reinterpret_cast<const double2*>(ra);
                 const double2* pb = reinterpret_cast<const double2*>(rb);
-                for (int kk = 0; kk < N / 2; ++kk) {
+                // every lane walks its own two rows (32 sectors per load instruction): eight loads in flight per lane ahead of
+                // the dependent chain of additions, whose order stays k = 0, 1, 2, ...
+                int kk = 0;
+                for (; kk + 4 <= N / 2; kk += 4) {
+                    double2 va[4], vb[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { va[q] = pa[kk + q]; vb[q] = pb[kk + q]; }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double d0 = __dsub_rn(va[q].x, vb[q].x), d1 = __dsub_rn(va[q].y, vb[q].y);
+                        acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+                        acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+                    }
+                }
+                for (; kk < N / 2; ++kk) {
                     const double2 va = pa[kk], vb = pb[kk];
                     const double d0 = __dsub_rn(va.x, vb.x), d1 = __dsub_rn(va.y, vb.y);
                     acc = __dadd_rn(acc, __dmul_rn(d0, d0));

@@ -40,13 +40,26 @@ __global__ void __launch_bounds__(256) nco_dist_kernel(const double* __restrict_
         if (row >= N) return;
         const double si = sg[row];
         double nrm = 0.0;
-        for (int j = lane; j < N; j += 32) {
-            double r = __ddiv_rn(c[(size_t)row * N + j], __dmul_rn(si, sg[j]));
-            r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
-            if (r != r) r = 0.0;  // corr.fillna(0)
-            const double v = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
-            d[(size_t)row * N + j] = v;
-            nrm = fma(v, v, nrm);
+        // 8 independent loads per lane ahead of the divisions / square roots (as in hrp_dist_kernel); nrm keeps its order
+        for (int j0 = lane; j0 < N; j0 += 256) {
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + 32 * u;
+                x[u] = (j < N) ? c[(size_t)row * N + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + 32 * u;
+                if (j < N) {
+                    double r = __ddiv_rn(x[u], __dmul_rn(si, sg[j]));
+                    r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+                    if (r != r) r = 0.0;  // corr.fillna(0)
+                    const double v = sqrt(__dmul_rn(__dsub_rn(1.0, r), 0.5));
+                    d[(size_t)row * N + j] = v;
+                    nrm = fma(v, v, nrm);
+                }
+            }
         }
         nrm = warp_sum(nrm);           // squared row norm for the Gram form of the row distances
         if (lane == 0) rn[(size_t)s * N + row] = nrm;

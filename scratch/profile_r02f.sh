@@ -14,4 +14,9 @@ ncu --set full --clock-control none \
     -k regex:"sb2st|syrk|trmm|hrp_gram|eigvals|mpfit|markowitz|philox|reconstruct|backtransform|q2back|corr_kernel|hrp_prim|hrp_dist|hrp_tree|inviter" \
     -s 20 -c 18 -o gpurun_out/prof_r02f -f \
     python bench.py --steps 1 --warmup 1 --sims-per-step 592 --no-cpu-baseline --no-e2e --no-configs > gpurun_out/ncu_full_r02f.log 2>&1
-ls -la gpurun_out/ | tail -8
+# gpurun_out/ travels back only below 64 MiB: summarise the big report here and keep the CSV, not the report
+python tools/ncu_summaries.py kernels gpurun_out/prof_r02f.ncu-rep > gpurun_out/kernels_r02f.md
+python tools/ncu_summaries.py kernels gpurun_out/prof_r02f_s3.ncu-rep > gpurun_out/kernels_r02f_s3.md
+ncu -i gpurun_out/prof_r02f.ncu-rep --page raw --csv > gpurun_out/kernels_r02f_raw.csv
+rm -f gpurun_out/prof_r02f.ncu-rep
+ls -la gpurun_out/ | tail -12

@@ -2,7 +2,8 @@
  * allocation algebra given a partition: pinned by the reference's goldens (tests/test_optimizer.py:30-47) -> 1e-7,
    and vs the oracle 1e-9;
  * KMeans/silhouette search: parity UNPINNED vs the reference's sklearn 0.22.1; the kernel follows sklearn
-   1.9's algorithm and the agreement of its partitions with sklearn's is measured here."""
+   1.9's algorithm; its partitions must be sklearn 1.9's here (all but at most one of 12) and in >= 98 % of the 500
+   simulations of tests/test_gpu_configs.py::test_nco_partition_agreement_rate_config4_shape."""
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose, assert_array_almost_equal
@@ -80,7 +81,7 @@ def test_nco_clustering_agreement_with_sklearn():
         assert_allclose(w[i], oracle.nco(mus[i], covs[i], labels=got), rtol=1e-8, atol=1e-11)
         agree += _same_partition(got, ref_labels)
     print(f"NCO partition agreement with sklearn {agree}/{s}")
-    assert agree >= s // 2
+    assert agree >= s - 1          # 500 / 500 over the wider sample of tests/test_gpu_configs.py
 
 
 def test_nco_through_plugin_class(stock):

@@ -38,6 +38,8 @@ def launches(csv_path, bench_path):
     print("| kernel | launches | total ms | share (ncu) | share (bench events) |\n|---|---|---|---|---|")
     for n, (c, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
         key = n.replace("void ", "").split("<")[0].replace("trmm2_kernel", "trmm_kernel")
+        key = {"s3_pass_kernel": "sy2sb_pass_kernel", "s3_panel_kernel": "sy2sb_panel_kernel",
+               "backtransform_wy_kernel": "backtransform_kernel"}.get(key, key)
         print(f"| {n[:60]} | {c} | {ms:.3f} | {ms / total:.4f} | {bench.get(key, '')} |")
 
 
