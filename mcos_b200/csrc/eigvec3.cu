@@ -80,10 +80,38 @@ __global__ void __launch_bounds__(64) inviter_kernel(const double* __restrict__ 
         h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
         y[i * G] = ((double)(h & 0xffffff) + 0.5) / 8388608.0 - 1.0;
     }
+    // Every step of the two substitutions needs operands from global memory (the interleaved factor arrays) that do NOT depend
+    // on the recurrence, but the compiler keeps each load behind the previous step's store: a thread paid a DRAM round trip per
+    // step (~3300 cycles, all 16 N threads of a wave resident and waiting).  The operands of IV_PF steps are loaded together
+    // ahead of the dependent chain; reads and writes of y keep their order per element (y[i + 1] is read before the step
+    // that overwrites it).
+    constexpr int IV_PF = 8;
     double scale = 1.0;
     for (int sweep = 0; sweep < 3; ++sweep) {
         double bi = y[0] * scale;
-        for (int i = 0; i + 1 < N; ++i) {
+        int i = 0;
+        for (; i + IV_PF < N; i += IV_PF) {
+            double bnv[IV_PF], fv[IV_PF];
+            unsigned char pvv[IV_PF];
+#pragma unroll
+            for (int q = 0; q < IV_PF; ++q) {
+                bnv[q] = y[(size_t)(i + q + 1) * G];
+                fv[q] = dl[(size_t)(i + q) * G];
+                pvv[q] = pv[(size_t)(i + q) * G];
+            }
+#pragma unroll
+            for (int q = 0; q < IV_PF; ++q) {
+                const double bn = bnv[q] * scale;
+                if (pvv[q] == 0) {
+                    y[(size_t)(i + q) * G] = bi;
+                    bi = bn - fv[q] * bi;
+                } else {
+                    y[(size_t)(i + q) * G] = bn;
+                    bi = bi - fv[q] * bn;
+                }
+            }
+        }
+        for (; i + 1 < N; ++i) {
             const double bn = y[(size_t)(i + 1) * G] * scale;
             const double f = dl[i * G];
             if (pv[i * G] == 0) {
@@ -96,7 +124,26 @@ __global__ void __launch_bounds__(64) inviter_kernel(const double* __restrict__ 
         }
         double x1 = bi * ip[(size_t)(N - 1) * G], x2 = 0.0, mx = fabs(x1);
         y[(size_t)(N - 1) * G] = x1;
-        for (int i = N - 2; i >= 0; --i) {
+        i = N - 2;
+        for (; i - (IV_PF - 1) >= 0; i -= IV_PF) {
+            double yv[IV_PF], duv[IV_PF], du2v[IV_PF], ipv[IV_PF];
+#pragma unroll
+            for (int q = 0; q < IV_PF; ++q) {
+                yv[q] = y[(size_t)(i - q) * G];
+                duv[q] = du[(size_t)(i - q) * G];
+                du2v[q] = du2[(size_t)(i - q) * G];
+                ipv[q] = ip[(size_t)(i - q) * G];
+            }
+#pragma unroll
+            for (int q = 0; q < IV_PF; ++q) {
+                const double xi = (yv[q] - duv[q] * x1 - du2v[q] * x2) * ipv[q];
+                y[(size_t)(i - q) * G] = xi;
+                x2 = x1;
+                x1 = xi;
+                mx = fmax(mx, fabs(xi));
+            }
+        }
+        for (; i >= 0; --i) {
             const double xi = (y[i * G] - du[i * G] * x1 - du2[i * G] * x2) * ip[i * G];
             y[i * G] = xi;
             x2 = x1;
@@ -423,7 +470,9 @@ __global__ void __launch_bounds__(NW * 32) backtransform_wy_kernel(const double*
 // grid = (ceil(N / 128), S), 256 threads: the CTA stages the signal eigenvectors in shared memory once (they are re-read
 // N / 32 times per simulation instead of N / 8 from L2), each warp owns 4 output rows and a lane walks the columns, so one
 // shared-memory load of v_sj feeds 4 FMAs.  r_i = lbar + sum_s c_s v_si^2 is the diagonal of the clipped matrix.
+#ifndef RC_ROWS
 #define RC_ROWS 2
+#endif
 #ifndef RC_CTA_ROWS
 #define RC_CTA_ROWS 128   // rows per CTA: the staging of the eigenvectors is amortised over 128 x N outputs
 #endif

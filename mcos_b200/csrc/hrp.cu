@@ -523,7 +523,33 @@ __global__ void __launch_bounds__(TR_THREADS, 8) hrp_tree_kernel(const double* _
             const double* ra = D + (size_t)max(a, b) * N;
             const double* rb = D + (size_t)min(a, b) * N;
             double acc = 0.0;
-            if ((N & 1) == 0) {                 // rows are 16-byte aligned: half the load instructions (each touches 32 lines)
+            if ((N & 3) == 0) {
+                // rows are 32-byte aligned: one whole sector per lane and load (LDG.256).  Every lane walks its own two rows,
+                // so a load instruction is 32 sector look-ups whatever its width, and the kernel is bound by exactly that
+                // (L1 wavefronts: ~1 us per simulation with 16-byte loads)
+                int kk = 0;
+                for (; kk + 8 <= N; kk += 8) {
+                    double va[8], vb[8];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                     : "=d"(va[4 * q]), "=d"(va[4 * q + 1]), "=d"(va[4 * q + 2]), "=d"(va[4 * q + 3])
+                                     : "l"(ra + kk + 4 * q));
+                        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                     : "=d"(vb[4 * q]), "=d"(vb[4 * q + 1]), "=d"(vb[4 * q + 2]), "=d"(vb[4 * q + 3])
+                                     : "l"(rb + kk + 4 * q));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double df = __dsub_rn(va[q], vb[q]);
+                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                    }
+                }
+                for (; kk < N; ++kk) {
+                    const double df = __dsub_rn(ra[kk], rb[kk]);
+                    acc = __dadd_rn(acc, __dmul_rn(df, df));
+                }
+            } else if ((N & 1) == 0) {          // rows are 16-byte aligned: half the load instructions (each touches 32 lines)
                 const double2* pa = reinterpret_cast<const double2*>(ra);
                 const double2* pb = reinterpret_cast<const double2*>(rb);
                 // every lane walks its own two rows (32 sectors per load instruction): eight loads in flight per lane ahead of
