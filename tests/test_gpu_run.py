@@ -74,6 +74,18 @@ def test_run_is_independent_of_wave_and_batch_split():
     assert np.array_equal(a, b) and np.array_equal(a, np.concatenate([c0, c1]))
 
 
+def test_automatic_waves_are_equal_and_do_not_change_results():
+    """More simulations than one automatic wave (capped at 8192): mcosb_run cuts the job into equal waves rounded to the SM
+    count instead of full waves plus a short remainder; every simulation must come out as in an explicit small-wave run."""
+    mu, cov = block_diagonal_truth(20, n_blocks=2)
+    eng = Engine(20, 40, seed=3)
+    eng.set_truth(mu, cov)
+    s = 17000                                             # 3 automatic waves
+    a, sa = eng.run(_plan(0, True, [0, 1], 1, wave=0), s)
+    b, sb = eng.run(_plan(0, True, [0, 1], 1, wave=2999), s)
+    assert np.array_equal(a, b, equal_nan=True) and np.array_equal(sa, sb)
+
+
 def test_simulate_optimizations_readme_sample(stock):
     """BASELINE config 1: the README sample (reference README.md / tests/test_mcos.py shape): 20 stocks, MuCov,
     DeNoiser, Markowitz + HRP, VarianceErrorEstimator -> DataFrame[mean, stdev] indexed by optimizer."""
