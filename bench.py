@@ -300,6 +300,12 @@ def run_other_configs(args, mb, local, rank, world, barrier, drop_engines):
                   sim=mb.MuCovLedoitWolfObservationSimulator,
                   opts=[mb.MarkowitzOptimizer(), mb.HRPOptimizer(), mb.NCOOptimizer(10, 10), mb.RiskParityOptimizer()],
                   ests=three, trs=[mb.DeNoiserCovarianceTransformer()]),
+        "5_without_nco": dict(desc="config 5 without the NCO optimizer (Markowitz+HRP+RiskParity, three estimators in one pass): "
+                                   "%d sims per GPU" % args.config5_sims,
+                              mu=mu1k, cov=cov1k, t=2000, n_sims=args.config5_sims * world, check=1,
+                              sim=mb.MuCovLedoitWolfObservationSimulator,
+                              opts=[mb.MarkowitzOptimizer(), mb.HRPOptimizer(), mb.RiskParityOptimizer()],
+                              ests=three, trs=[mb.DeNoiserCovarianceTransformer()]),
     }
     out = {}
     for key, c in cases.items():

@@ -1,4 +1,6 @@
 // Context lifetime, truth upload (+ one-off Cholesky), and the error-estimator kernel (K5).
+#include <cstdlib>
+
 #include "common.cuh"
 
 extern "C" int mcosb_version(void) { return 200; }
@@ -115,6 +117,73 @@ __global__ void __launch_bounds__(1024) chol_truth_kernel(double* __restrict__ L
     }
 }
 
+// Blocked left-looking form of the same factorisation (the end-to-end path re-factorises the truth with every call: the
+// one-CTA kernel above is 5.1 ms at N = 500, 1500 block-wide barriers and 500 dependent L2 round trips).  Per panel of
+// CHP = 32 columns starting at p:
+//   chol_update_kernel   A[i][p + c] -= sum_{k < p} L[i][k] L[p + c][k] for the rows i >= p, 32 x 32 outputs per CTA, k in
+//                        chunks of 32 through shared memory (both operand tiles read coalesced along k);
+//   chol_panel_kernel    one CTA: the updated panel (N - p rows x 32 columns) in shared memory, 32 column steps (pivot,
+//                        scale, update of the columns to its right), written back; the upper triangle of its rows zeroed.
+// Exact zeros stay exact zeros (sums of products with zero), which is what the TRMM's slab list relies on.
+#define CHP 32
+__global__ void __launch_bounds__(CHP * CHP) chol_update_kernel(double* __restrict__ L, int n, int p) {
+    __shared__ double Li[CHP][CHP + 1], Lc[CHP][CHP + 1];
+    const int tc = threadIdx.x & (CHP - 1), ti = threadIdx.x / CHP;
+    const int i0 = p + blockIdx.x * CHP;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < p; k0 += CHP) {
+        const int k = k0 + tc;            // lanes along k: coalesced
+        Li[ti][tc] = (i0 + ti < n && k < p) ? L[(size_t)(i0 + ti) * n + k] : 0.0;
+        Lc[ti][tc] = (p + ti < n && k < p) ? L[(size_t)(p + ti) * n + k] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CHP; ++kk) acc = fma(Li[ti][kk], Lc[tc][kk], acc);
+        __syncthreads();
+    }
+    const int i = i0 + ti, j = p + tc;
+    if (i < n && j < n && j <= i) L[(size_t)i * n + j] -= acc;
+}
+
+__global__ void __launch_bounds__(1024) chol_panel_kernel(double* __restrict__ L, int n, int p, int* __restrict__ flag) {
+    extern __shared__ double P[];         // [(n - p)][CHP + 1]
+    __shared__ double s_piv;
+    const int m = n - p, w = min(CHP, n - p), tid = threadIdx.x;
+    for (int idx = tid; idx < m * CHP; idx += 1024) {
+        const int r = idx / CHP, c = idx % CHP;
+        P[r * (CHP + 1) + c] = (c < w && c <= r) ? L[(size_t)(p + r) * n + p + c] : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < w; ++c) {
+        if (tid == 0) {
+            double v = P[c * (CHP + 1) + c];
+            if (!(v > 0.0)) { flag[0] = 1; v = 1.0; }
+            v = sqrt(v);
+            P[c * (CHP + 1) + c] = v;
+            s_piv = v;
+        }
+        __syncthreads();
+        const double piv = s_piv;
+        for (int r = c + 1 + tid; r < m; r += 1024) P[r * (CHP + 1) + c] /= piv;
+        __syncthreads();
+        // columns c + 1 .. w - 1 of the rows below: P[r][c2] -= P[r][c] P[c2][c]
+        const int nc = w - c - 1;
+        for (int idx = tid; idx < (m - c - 1) * nc; idx += 1024) {
+            const int r = c + 1 + idx / nc, c2 = c + 1 + idx % nc;
+            if (c2 <= r) P[r * (CHP + 1) + c2] = fma(-P[r * (CHP + 1) + c], P[c2 * (CHP + 1) + c], P[r * (CHP + 1) + c2]);
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < m * CHP; idx += 1024) {
+        const int r = idx / CHP, c = idx % CHP;
+        if (c < w && c <= r) L[(size_t)(p + r) * n + p + c] = P[r * (CHP + 1) + c];
+    }
+    // upper triangle of the panel's rows
+    for (int idx = tid; idx < w * n; idx += 1024) {
+        const int r = idx / n, j = idx % n;
+        if (j > p + r) L[(size_t)(p + r) * n + j] = 0.0;
+    }
+}
+
 // The k-slabs of L a TRMM column tile has to visit (ctx->d_klist): one CTA per tile of 64 rows of L, one thread per slab of
 // 16 columns up to the diagonal; the non-empty ones are listed in ascending order.  Dense factors list every slab up to
 // the diagonal, which is what the TRMM walked before the list existed.
@@ -170,8 +239,22 @@ extern "C" int mcosb_set_truth(mcosb_ctx* ctx, const double* mu, const double* c
     int* dflag = nullptr;
     MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, 1, &dflag));
     MCOSB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
-    chol_truth_kernel<<<1, 1024, n * sizeof(double), ctx->stream>>>(ctx->d_chol, ctx->N, dflag);
-    MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
+    const size_t smem_panel = n * (CHP + 1) * sizeof(double);
+    static const bool chol_one_cta = getenv("MCOSB_CHOL_ONE_CTA") != nullptr;   // the one-CTA kernel (A/B runs)
+    if (!chol_one_cta && smem_panel <= (size_t)ctx->smem_optin) {
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel));
+        for (int p = 0; p < ctx->N; p += CHP) {
+            if (p > 0) {
+                chol_update_kernel<<<(ctx->N - p + CHP - 1) / CHP, CHP * CHP, 0, ctx->stream>>>(ctx->d_chol, ctx->N, p);
+                MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
+            }
+            chol_panel_kernel<<<1, 1024, (size_t)(ctx->N - p) * (CHP + 1) * sizeof(double), ctx->stream>>>(ctx->d_chol, ctx->N, p, dflag);
+            MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
+        }
+    } else {
+        chol_truth_kernel<<<1, 1024, n * sizeof(double), ctx->stream>>>(ctx->d_chol, ctx->N, dflag);
+        MCOSB_LAUNCHED(ctx, MK_CHOL_TRUTH);
+    }
     const int n_tiles = (ctx->N + 63) / 64;
     MCOSB_CUDA(ctx, cudaMemsetAsync(ctx->d_nk + n_tiles, 0, sizeof(int), ctx->stream));
     chol_slab_list_kernel<<<n_tiles, 128, 0, ctx->stream>>>(ctx->d_chol, ctx->N, ctx->d_klist, ctx->d_nk);
