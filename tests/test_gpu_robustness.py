@@ -85,3 +85,27 @@ def test_truth_below_the_risk_free_rate_runs_and_is_reported():
     assert mb.status_counts(status) == {"NO_EXCESS": 8}
     tab = mb.summarize_errors(errs, [mb.MarkowitzOptimizer(), mb.HRPOptimizer()], status=status)
     assert (tab["n_flagged"] == 8).all()
+
+
+@pytest.mark.parametrize("n", [20, 100, 257, 500])
+def test_truth_without_a_cholesky_factor_is_refused_by_both_factorisations(n):
+    """mcosb_set_truth factorises the truth in blocked form (32-column panels; one-CTA kernel when the panel does not fit
+    shared memory): an indefinite truth -- non-positive pivot in the first panel, in a later one, on the last column --
+    must come back as MCOSB_ERR_NOT_PD (-4) and a definite one must factorise to numpy's factor."""
+    from mcos_b200._lib import MCOSBError as MCOSError
+    rng = np.random.RandomState(n)
+    a = rng.standard_normal((n, 2 * n))
+    good = a @ a.T / (2 * n)
+    mu = np.zeros(n)
+    eng = Engine(n, 8, seed=1)
+    for bad_at in (0, n // 2, n - 1):
+        bad = good.copy()
+        bad[bad_at, bad_at] = -1.0 if bad_at == 0 else good[bad_at, :bad_at] @ np.linalg.solve(good[:bad_at, :bad_at], good[:bad_at, bad_at]) - 1e-3
+        with pytest.raises(MCOSError):
+            eng.set_truth(mu, bad)
+        eng.set_truth(mu, bad, require_pd=False)          # accepted for the estimators, sampling still refused
+    eng.set_truth(mu, good)
+    x = eng.sample(1)
+    from philox_ref import standard_normals
+    want = standard_normals([0], 8, n, 1)[0] @ np.linalg.cholesky(good).T
+    np.testing.assert_allclose(x[0], want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
