@@ -20,6 +20,7 @@ enum ScratchSlot {
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
     SL_NCO_W, SL_NCO_LABELS, SL_NCO_WORK, SL_NCO_E,
     SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2, SL_NCO_CENTERS, SL_S2_ZP, SL_S2_ZC, SL_S3_V, SL_S3_W, SL_S3_GT, SL_S3_ZP,
+    SL_ZSUM_PART, SL_ZBAR,
     SL_COUNT
 };
 
@@ -314,14 +315,21 @@ __device__ __forceinline__ double lw_shrink(double c, double sh, double m, bool 
 // internal (device-pointer) stage entry points used by the public wrappers and by mcosb_run
 // ---------------------------------------------------------------------------------------------------------------
 // add_mu = false: dX receives Y = Z L' = X - mu (the draws centred by the TRUE mean), for mcosb_dev_moments(..., shift = true mu)
-int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool add_mu = true);
+// dybar != nullptr (with add_mu = false): the column means of Y are produced on the way -- the normal generator sums the columns
+// of Z while it writes them, and zbar rides through the TRMM as one more row per simulation behind the last draw: ybar = zbar L'
+// lands at dX + S T N (dX must have room for S (T + 1) N doubles), *dybar points there, mu + ybar goes to dmu_out[S][N]; *have_ybar
+// tells whether that happened (N small enough for the generator's shared-memory sums), so that mcosb_dev_moments can skip its mean
+// pass over X.
+int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool add_mu = true, double** dybar = nullptr,
+                     double* dmu_out = nullptr, bool* have_ybar = nullptr);
 // lwcoef_defer (Ledoit-Wolf only): instead of shrinking dcov in place, leave S_b there and write (shrinkage, mean
 // variance) per simulation to lwcoef_defer[2 s .. 2 s + 1]; mcosb_dev_denoise applies them while it forms the correlation
 // shift (device, [N]) != nullptr: dX holds the draws MINUS this vector (mcosb_dev_sample with add_mu = false); the means get
 // it added back, and the covariance is formed as (Y'Y - T ybar ybar') / (T - 1) without centring in the GEMM loop -- exact
 // algebra, and well conditioned because ybar is O(sigma / sqrt(T)).
+// ybar_pre (with shift): the column means of dX are already known (mcosb_dev_sample) and dmu is already written.
 int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink,
-                      double* lwcoef_defer = nullptr, const double* shift = nullptr);
+                      double* lwcoef_defer = nullptr, const double* shift = nullptr, const double* ybar_pre = nullptr);
 int mcosb_dev_denoise(mcosb_ctx* ctx, int S, double* dcov, int n_obs, double bandwidth, double* deig, double* dvar,
                       int* dnf, int* dstatus, const double* lwcoef = nullptr);
 // *q2 receives the stage-2 reflectors when the two-stage tridiagonalisation was used (then A holds the panel reflectors

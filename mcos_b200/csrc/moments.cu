@@ -301,7 +301,7 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
 }
 
 int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double* dmu, double* dcov, double* dshrink,
-                      double* lwcoef_defer, const double* shift) {
+                      double* lwcoef_defer, const double* shift, const double* ybar_pre) {
     if (kind < 0 || kind > 2) return mcosb_fail(ctx, MCOSB_ERR_ARG, "unknown moments kind");
     if (S == 0) return MCOSB_OK;
     const int N = ctx->N, T = ctx->T;
@@ -312,10 +312,14 @@ int mcosb_dev_moments(mcosb_ctx* ctx, int S, const double* dX, int kind, double*
 
     // with a shift the statistics are taken of Y = X - shift: ybar in scratch, shift + ybar reported as the mean
     double* dmean = dmu;
-    if (shift) MCOSB_TRY(mcosb_scratch_t(ctx, SL_COLMEAN, (size_t)S * N, &dmean));
-    dim3 gm((N + CM_COLS - 1) / CM_COLS, S);
-    colmean_kernel<<<gm, CM_COLS * CM_ROWGROUPS, 0, ctx->stream>>>(dX, T, N, dmean, shift, dmu);
-    MCOSB_LAUNCHED(ctx, MK_COLMEAN);
+    if (shift && ybar_pre) {
+        dmean = const_cast<double*>(ybar_pre);      // the sampler summed the columns on the way: no mean pass over X
+    } else {
+        if (shift) MCOSB_TRY(mcosb_scratch_t(ctx, SL_COLMEAN, (size_t)S * N, &dmean));
+        dim3 gm((N + CM_COLS - 1) / CM_COLS, S);
+        colmean_kernel<<<gm, CM_COLS * CM_ROWGROUPS, 0, ctx->stream>>>(dX, T, N, dmean, shift, dmu);
+        MCOSB_LAUNCHED(ctx, MK_COLMEAN);
+    }
 
     const int nt = (N + DM_BM - 1) / DM_BM, ntiles = 2 * (nt * (nt + 1) / 2);   // two CTAs per 128 x 128 tile
     double* lwpart = nullptr;

@@ -67,8 +67,8 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, const RunPlan& rp, ui
     const size_t chunk_bytes = RUN_CHUNK_BYTES;
     int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)W, chunk_bytes / (T * N * sizeof(double))));
     CH = (W + (W + CH - 1) / CH - 1) / ((W + CH - 1) / CH);   // the same number of sub-chunks, equal sizes
-    double* dX;
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * T * N, &dX));
+    double *dX, *dyb = nullptr;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * (T + 1) * N, &dX));   // + one row per simulation: the column means
     // Ledoit-Wolf followed by the de-noiser: the shrink (one read-modify-write of every covariance matrix) is folded
     // into the de-noiser's covariance -> correlation pass, which is the only consumer of the shrunk matrix
     double* lwcoef = nullptr;
@@ -79,11 +79,13 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, const RunPlan& rp, ui
         MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, true));
         // the draws stay centred by the TRUE mean (Y = Z L'): the moment kernels add it back to the sample mean and take the
         // covariance of Y without centring inside the GEMM loop (mcosb_sample_moments is the same pair as a stage call)
-        MCOSB_TRY(mcosb_dev_sample(ctx, sim0 + c0, nc, dX, false));
+        // ... and their column means come out of the sampler (sums of Z while it is written, then zbar L'): no mean pass
+        bool have_ybar = false;
+        MCOSB_TRY(mcosb_dev_sample(ctx, sim0 + c0, nc, dX, false, &dyb, dmu + (size_t)c0 * N, &have_ybar));
         MCOSB_TRY(mark(MCOSB_STAGE_SAMPLE, false));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, true));
         MCOSB_TRY(mcosb_dev_moments(ctx, nc, dX, plan->moments_kind, dmu + (size_t)c0 * N, dcov + (size_t)c0 * N * N,
-                                    nullptr, lwcoef ? lwcoef + 2 * (size_t)c0 : nullptr, ctx->d_mu));
+                                    nullptr, lwcoef ? lwcoef + 2 * (size_t)c0 : nullptr, ctx->d_mu, have_ybar ? dyb : nullptr));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, false));
     }
     for (int i = 0; i < rp.ntr; ++i) {   // any list, in order (mcos.py:25-26)
@@ -143,13 +145,14 @@ extern "C" int mcosb_sample_moments(mcosb_ctx* ctx, uint64_t sim_id0, int S, int
     MCOSB_TRY(st.out(shrink, (size_t)S, SL_STAGE_OUT2, &dsh));
     if (S > 0) {
         const int CH = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, (size_t)RUN_CHUNK_BYTES / (T * N * sizeof(double))));
-        double* dX;
-        MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * T * N, &dX));
+        double *dX, *dyb = nullptr;
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_X, (size_t)CH * (T + 1) * N, &dX));
         for (int c0 = 0; c0 < S; c0 += CH) {
             const int nc = std::min(CH, S - c0);
-            MCOSB_TRY(mcosb_dev_sample(ctx, sim_id0 + c0, nc, dX, false));
+            bool have_ybar = false;
+            MCOSB_TRY(mcosb_dev_sample(ctx, sim_id0 + c0, nc, dX, false, &dyb, dmu + (size_t)c0 * N, &have_ybar));
             MCOSB_TRY(mcosb_dev_moments(ctx, nc, dX, kind, dmu + (size_t)c0 * N, dcov + (size_t)c0 * N * N,
-                                        dsh ? dsh + c0 : nullptr, nullptr, ctx->d_mu));
+                                        dsh ? dsh + c0 : nullptr, nullptr, ctx->d_mu, have_ybar ? dyb : nullptr));
         }
     }
     return st.finish();

@@ -70,6 +70,65 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(double* __restrict__
     }
 }
 
+// The same normals with their column sums: CTA (b, s) writes rows [b PRB, (b + 1) PRB) of simulation s, warp w the rows
+// b PRB + w, + 8, ...; every warp adds what it writes into its own shared-memory row of N sums, the CTA folds the eight rows
+// in warp order into part[s][b][N].  zbar_kernel adds the blocks in order and divides by T.  The column means of Y = Z L' are
+// then zbar L' -- one more row per simulation for the TRMM instead of a pass over the 8 T N bytes of Y (colmean_kernel).
+// Fixed summation order: bit-reproducible.
+#define PRB 128
+__global__ void __launch_bounds__(256) philox_normal_sums_kernel(double* __restrict__ Z, uint64_t sim_id0, int T, int N,
+                                                                 uint64_t seed, double* __restrict__ part) {
+    extern __shared__ double zacc[];               // [8][N2], N2 = 2 P
+    const uint32_t P = (uint32_t)(N + 1) / 2;
+    const int N2 = 2 * (int)P;
+    const int s = blockIdx.y, b = blockIdx.x, nblk = gridDim.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t0 = b * PRB, t1 = min(T, t0 + PRB);
+    const bool vec = (N & 1) == 0 && ((uintptr_t)Z & 15) == 0;
+    double* mine = zacc + (size_t)wid * N2;
+    for (uint32_t p = lane; p < P; p += 32) mine[2 * p] = mine[2 * p + 1] = 0.0;      // the pairs this lane will add to
+    for (int t = t0 + (int)wid; t < t1; t += 8) {
+        double* dst = Z + ((size_t)s * T + t) * N;
+        for (uint32_t p = lane; p < P; p += 32) {
+            double z0, z1;
+            normal_pair(sim_id0 + s, (uint32_t)t, p, seed, z0, z1);
+            if (vec) {
+                reinterpret_cast<double2*>(dst)[p] = make_double2(z0, z1);
+            } else {
+                dst[2 * p] = z0;
+                if (2 * p + 1 < (uint32_t)N) dst[2 * p + 1] = z1;
+            }
+            double2 a = *reinterpret_cast<double2*>(mine + 2 * p);
+            a.x += z0;
+            a.y += z1;                             // column N of an odd N is never read back
+            *reinterpret_cast<double2*>(mine + 2 * p) = a;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += 256) {
+        double tot = zacc[i];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) tot += zacc[(size_t)w * N2 + i];
+        part[((size_t)s * nblk + b) * N + i] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(256) zbar_kernel(const double* __restrict__ part, int nblk, int T, int N,
+                                                   double* __restrict__ zbar) {
+    const int s = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    double tot = 0.0;
+    for (int b = 0; b < nblk; ++b) tot += part[((size_t)s * nblk + b) * N + i];
+    zbar[(size_t)s * N + i] = tot / (double)T;
+}
+
+// sample mean = true mean + ybar
+__global__ void __launch_bounds__(256) add_shift_kernel(const double* __restrict__ ybar, const double* __restrict__ mu, int N,
+                                                        size_t n, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = mu[i % N] + ybar[i];
+}
+
 // X[m][j] = mu[j] + sum_{k <= j} Z[m][k] L[j][k];  M = S*T rows.  grid = (col tiles, row tiles)
 // VEC: 16-byte cp.async (N even, Z and L 16-byte aligned), otherwise 8-byte copies.
 template <bool VEC>
@@ -247,33 +306,14 @@ trmm2_kernel(const double* __restrict__ Z, const double* __restrict__ L, const d
         }
 }
 
-int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool add_mu) {
-    if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
-    if (S == 0) return MCOSB_OK;
-    const int N = ctx->N, T = ctx->T;
-    const size_t M = (size_t)S * T;
-    double* dZ = nullptr;
-    MCOSB_TRY(mcosb_scratch_t(ctx, SL_Z, M * N, &dZ));
-    int grid = (int)std::min<size_t>((M + 7) / 8, (size_t)ctx->num_sms * PHILOX_CTAS_PER_SM);   // 8 warps = 8 rows per CTA and pass
-    philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
-    MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
-    size_t row_tiles = (M + DM_BM - 1) / DM_BM;
+// X = (mu +) Z L' for M rows of Z through trmm2_kernel (the 128 x 64 / 4-warp TRMM)
+static int launch_trmm2(mcosb_ctx* ctx, const double* dZ, size_t M, double* dX, bool add_mu) {
+    const int N = ctx->N;
+    const size_t row_tiles = (M + DM_BM - 1) / DM_BM;
     if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");
     const bool vec = N % 2 == 0 && (uintptr_t)dZ % 16 == 0 && (uintptr_t)ctx->d_chol % 16 == 0 && (uintptr_t)dX % 16 == 0;
-    static const bool one_cta = std::getenv("MCOSB_TRMM_256") != nullptr;   // the 128 x 128 / 256-thread variant (A/B runs)
-    if (one_cta && add_mu) {
-        const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
-        dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
-        if (vec) {
-            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            trmm_kernel<true><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
-        } else {
-            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            trmm_kernel<false><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
-        }
-    } else {
-        const size_t smem = (size_t)DM_STAGES * T2_STAGE * sizeof(double);
-        dim3 g((N + T2_BN - 1) / T2_BN, (unsigned)row_tiles);
+    const size_t smem = (size_t)DM_STAGES * T2_STAGE * sizeof(double);
+    dim3 g((N + T2_BN - 1) / T2_BN, (unsigned)row_tiles);
 #define T2_LAUNCH(V, A, SP)                                                                                           \
     do {                                                                                                              \
         MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm2_kernel<V, A, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -285,14 +325,67 @@ int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool a
         if (ctx->chol_sparse) T2_LAUNCH(V, A, true);                                                                  \
         else T2_LAUNCH(V, A, false);                                                                                  \
     } while (0)
-        if (vec && add_mu) T2_LAUNCH2(true, true);
-        else if (vec) T2_LAUNCH2(true, false);
-        else if (add_mu) T2_LAUNCH2(false, true);
-        else T2_LAUNCH2(false, false);
+    if (vec && add_mu) T2_LAUNCH2(true, true);
+    else if (vec) T2_LAUNCH2(true, false);
+    else if (add_mu) T2_LAUNCH2(false, true);
+    else T2_LAUNCH2(false, false);
 #undef T2_LAUNCH2
 #undef T2_LAUNCH
-    }
     MCOSB_LAUNCHED(ctx, MK_TRMM);
+    return MCOSB_OK;
+}
+
+int mcosb_dev_sample(mcosb_ctx* ctx, uint64_t sim_id0, int S, double* dX, bool add_mu, double** dybar, double* dmu_out,
+                     bool* have_ybar) {
+    if (have_ybar) *have_ybar = false;
+    if (!ctx->have_truth) return mcosb_fail(ctx, MCOSB_ERR_STATE, "mcosb_set_truth has not been called");
+    if (S == 0) return MCOSB_OK;
+    const int N = ctx->N, T = ctx->T;
+    const size_t M = (size_t)S * T;
+    double* dZ = nullptr;
+    MCOSB_TRY(mcosb_scratch_t(ctx, SL_Z, (M + S) * N, &dZ));      // + one row of column means per simulation
+    static const bool no_sums = std::getenv("MCOSB_NO_ZSUMS") != nullptr;   // A/B runs: mean pass over X instead
+    const size_t smem_sums = (size_t)8 * 2 * ((N + 1) / 2) * sizeof(double);
+    const int nblk = (T + PRB - 1) / PRB;
+    const bool sums = dybar && dmu_out && !add_mu && !no_sums && S <= 65535 && smem_sums <= (size_t)ctx->smem_optin;
+    double* part = nullptr;
+    if (sums) {
+        MCOSB_TRY(mcosb_scratch_t(ctx, SL_ZSUM_PART, (size_t)S * nblk * N, &part));
+        MCOSB_CUDA(ctx, cudaFuncSetAttribute(philox_normal_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sums));
+        philox_normal_sums_kernel<<<dim3(nblk, S), 256, smem_sums, ctx->stream>>>(dZ, sim_id0, T, N, ctx->seed, part);
+        MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
+        // zbar goes behind the last row of Z: the TRMM below turns it into ybar = zbar L' behind the last row of Y
+        zbar_kernel<<<dim3((N + 255) / 256, S), 256, 0, ctx->stream>>>(part, nblk, T, N, dZ + M * N);
+    } else {
+        int grid = (int)std::min<size_t>((M + 7) / 8, (size_t)ctx->num_sms * PHILOX_CTAS_PER_SM);   // 8 warps = 8 rows per CTA and pass
+        philox_normal_kernel<<<grid, 256, 0, ctx->stream>>>(dZ, sim_id0, S, T, N, ctx->seed);
+    }
+    MCOSB_LAUNCHED(ctx, MK_PHILOX_NORMAL);
+    static const bool one_cta = std::getenv("MCOSB_TRMM_256") != nullptr;   // the 128 x 128 / 256-thread variant (A/B runs)
+    if (one_cta && add_mu) {
+        size_t row_tiles = (M + DM_BM - 1) / DM_BM;
+        if (row_tiles > 65535) return mcosb_fail(ctx, MCOSB_ERR_ARG, "sample batch too large; split it");
+        const bool vec = N % 2 == 0 && (uintptr_t)dZ % 16 == 0 && (uintptr_t)ctx->d_chol % 16 == 0 && (uintptr_t)dX % 16 == 0;
+        const size_t smem = (size_t)DM_STAGES * 2 * DM_TILE_MMAJOR * sizeof(double);
+        dim3 g((N + DM_BN - 1) / DM_BN, (unsigned)row_tiles);
+        if (vec) {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trmm_kernel<true><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+        } else {
+            MCOSB_CUDA(ctx, cudaFuncSetAttribute(trmm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            trmm_kernel<false><<<g, DM_THREADS, smem, ctx->stream>>>(dZ, ctx->d_chol, ctx->d_mu, M, N, dX);
+        }
+        MCOSB_LAUNCHED(ctx, MK_TRMM);
+    } else {
+        MCOSB_TRY(launch_trmm2(ctx, dZ, sums ? M + S : M, dX, add_mu));
+    }
+    if (sums) {
+        *dybar = dX + M * N;
+        const size_t n = (size_t)S * N;
+        add_shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(*dybar, ctx->d_mu, N, n, dmu_out);
+        MCOSB_LAUNCHED(ctx, MK_COLMEAN);
+        if (have_ybar) *have_ybar = true;
+    }
     return MCOSB_OK;
 }
 
