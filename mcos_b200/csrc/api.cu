@@ -22,6 +22,16 @@ extern "C" int mcosb_create(mcosb_ctx** out, int device, int n_assets, int n_obs
         return MCOSB_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    {
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi_pri) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_ideal, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) != cudaSuccess) {
+            mcosb_destroy(ctx);
+            return MCOSB_ERR_CUDA;
+        }
+    }
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     size_t n = (size_t)n_assets;
@@ -50,6 +60,9 @@ extern "C" int mcosb_destroy(mcosb_ctx* ctx) {
     if (ctx->d_klist) cudaFree(ctx->d_klist);
     if (ctx->d_nk) cudaFree(ctx->d_nk);
     if (ctx->d_hrp_slow) cudaFree(ctx->d_hrp_slow);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->ev_ideal) cudaEventDestroy(ctx->ev_ideal);
+    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MCOSB_OK;

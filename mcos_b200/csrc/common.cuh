@@ -108,6 +108,11 @@ struct mcosb_ctx {
     uint64_t seed = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    // the ideal allocations on the true (mu, cov) -- a handful of one-CTA kernels, ~2 ms -- run on this stream while the first
+    // wave samples; the wave waits for ev_ideal before its first transformer / optimizer touches the scratch they share
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_ideal = nullptr, ev_main = nullptr;
+    bool ideal_pending = false;
     double* d_mu = nullptr;    // true mu [N]
     double* d_cov = nullptr;   // true cov [N][N]
     double* d_chol = nullptr;  // lower Cholesky factor of the true cov [N][N]

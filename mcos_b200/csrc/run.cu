@@ -88,6 +88,10 @@ int mcosb_run_wave(mcosb_ctx* ctx, const mcosb_plan* plan, const RunPlan& rp, ui
                                     nullptr, lwcoef ? lwcoef + 2 * (size_t)c0 : nullptr, ctx->d_mu, have_ybar ? dyb : nullptr));
         MCOSB_TRY(mark(MCOSB_STAGE_MOMENTS, false));
     }
+    if (ctx->ideal_pending) {            // the ideal allocations (auxiliary stream) share scratch with the stages below
+        MCOSB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ideal, 0));
+        ctx->ideal_pending = false;
+    }
     for (int i = 0; i < rp.ntr; ++i) {   // any list, in order (mcos.py:25-26)
         MCOSB_TRY(mark(MCOSB_STAGE_DENOISE, true));
         if (rp.tr_kind[i] == MCOSB_TR_DENOISE)
@@ -186,6 +190,10 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
     else MCOSB_TRY(mcosb_scratch_t(ctx, SL_STATUS, (size_t)S, &dstatus));
     MCOSB_CUDA(ctx, cudaMemsetAsync(dstatus, 0, (size_t)S * sizeof(int), ctx->stream));
 
+    if (ctx->ideal_pending) {   // left over from a call that failed before its first wave
+        MCOSB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ideal, 0));
+        ctx->ideal_pending = false;
+    }
     MCOSB_PROFILE_MARK(ctx);
     // ---- ideal allocations on the true (mu, cov): once per (truth, optimizer list), kept in the context -----------------
     double* d_ideal;
@@ -197,6 +205,21 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
              plan->optimizers[2], plan->optimizers[3], plan->risk_free_rate, plan->nco_max_clusters, plan->nco_trials);
     if (ctx->ideal_key != key || rp.d_budget) {   // a custom risk budget is not part of the key: recompute
         ctx->ideal_key.clear();
+        // On the auxiliary (high-priority) stream, behind everything already queued on the main one: the one-CTA kernels of
+        // the ideal allocation then overlap the sampling of the first wave instead of idling the GPU ahead of it.  With
+        // per-kernel profiling on, everything stays on the main stream (a kernel's time is the gap between its events).
+        static const bool ideal_serial = getenv("MCOSB_IDEAL_SERIAL") != nullptr;
+        cudaStream_t main_stream = ctx->stream;
+        const bool overlap = !ctx->profile && !ideal_serial && ctx->aux_stream;
+        if (overlap) {
+            MCOSB_CUDA(ctx, cudaEventRecord(ctx->ev_main, main_stream));
+            MCOSB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_main, 0));
+            ctx->stream = ctx->aux_stream;
+        }
+        struct Restore {
+            mcosb_ctx* c; cudaStream_t s;
+            ~Restore() { c->stream = s; }
+        } restore{ctx, main_stream};
         MCOSB_CUDA(ctx, cudaMemsetAsync(d_ideal_status, 0, sizeof(int), ctx->stream));
         for (int o = 0; o < nopt; ++o) {
             double* wi = d_ideal + (size_t)o * N;
@@ -210,6 +233,10 @@ extern "C" int mcosb_run(mcosb_ctx* ctx, const mcosb_plan* plan, uint64_t sim_id
             else
                 MCOSB_TRY(mcosb_dev_nco(ctx, 1, ctx->d_mu, ctx->d_cov, plan->nco_max_clusters, plan->nco_trials, nullptr, wi,
                                         nullptr, d_ideal_status));
+        }
+        if (overlap) {
+            MCOSB_CUDA(ctx, cudaEventRecord(ctx->ev_ideal, ctx->aux_stream));
+            ctx->ideal_pending = true;
         }
         if (!rp.d_budget) ctx->ideal_key = key;
     }
