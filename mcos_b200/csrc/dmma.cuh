@@ -13,8 +13,12 @@
 
 #define DM_BM 128
 #define DM_BN 128
+#ifndef DM_BK
 #define DM_BK 16
+#endif
+#ifndef DM_STAGES
 #define DM_STAGES 3
+#endif
 #define DM_THREADS 256
 #define DM_WM 64   // warp tile rows
 #define DM_WN 32   // warp tile cols
