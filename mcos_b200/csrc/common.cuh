@@ -20,7 +20,7 @@ enum ScratchSlot {
     SL_HRP_E, SL_HRP_W, SL_HRP_ORDER, SL_HRP_LINK, SL_HRP_WORK,
     SL_NCO_W, SL_NCO_LABELS, SL_NCO_WORK, SL_NCO_E,
     SL_ERR, SL_STATUS, SL_IDEAL, SL_RUN_W, SL_DN_Q2, SL_NCO_CENTERS, SL_S2_ZP, SL_S2_ZC, SL_S3_V, SL_S3_W, SL_S3_GT, SL_S3_ZP,
-    SL_ZSUM_PART, SL_ZBAR,
+    SL_ZSUM_PART,
     SL_COUNT
 };
 
